@@ -1,0 +1,225 @@
+// api.cu -- C ABI entry points for the single-GPU stages (include/dj_b200.h):
+// dj_hash_partition_i64 and dj_inner_join_i64, plus library bookkeeping.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "dj_device.cuh"
+#include "dj_internal.h"
+
+namespace dj {
+
+static thread_local char g_error[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches += n; }
+
+int sm_count()
+{
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    cached     = prop.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+namespace {
+
+__global__ void set_two_offsets(int64_t* a, int64_t na, int64_t* b, int64_t nb)
+{
+  a[0] = 0;
+  a[1] = na;
+  b[0] = 0;
+  b[1] = nb;
+}
+
+}  // namespace
+
+// scratch rows needed by the join's radix passes + offsets + pass workspace
+static size_t local_join_ws_bytes(int64_t nb, int64_t np)
+{
+  RadixPlan plan = make_radix_plan(nb);
+  const int levels = (plan.bits1 > 0) + (plan.bits2 > 0);
+  size_t total     = 4096;
+  total += (size_t)levels * (align_up((size_t)nb * 8, 256) * 2 + align_up((size_t)np * 8, 256) * 2);
+  total += 2 * align_up(((size_t)plan.nbuckets + 1) * 8, 256);
+  const int F1 = 1 << plan.bits1, F2 = 1 << plan.bits2;
+  total += 2 * align_up(((size_t)F1 + 1) * 8, 256);
+  size_t pw = pass_workspace_bytes(1, F1);
+  if (plan.bits2) {
+    size_t pw2 = pass_workspace_bytes(F1, F2);
+    if (pw2 > pw) pw = pw2;
+  }
+  total += 2 * pw;
+  return total + 4096;
+}
+
+// Joins (bk,bp)[nb] with (pk,pp)[np]; appends matches at *d_out_count (running, device).
+// out[] is always (left key, left payload, right key, right payload); when swap is true the
+// build side is the caller's RIGHT table.
+int local_join(const int64_t* bk, const int64_t* bp, int64_t nb, const int64_t* pk,
+               const int64_t* pp, int64_t np, int64_t* const out[4], int64_t out_capacity,
+               int64_t* d_out_count, bool swap, Arena& arena, cudaStream_t stream)
+{
+  if (nb == 0 || np == 0) return DJ_OK;  // src/distributed_join.cpp:76-82
+  const RadixPlan plan = make_radix_plan(nb);
+  const int F1 = 1 << plan.bits1, F2 = 1 << plan.bits2;
+
+  int* work_counter = arena.take<int>(64);
+  int64_t* boff     = arena.take<int64_t>((size_t)plan.nbuckets + 1);
+  int64_t* poff     = arena.take<int64_t>((size_t)plan.nbuckets + 1);
+  if (!work_counter || !boff || !poff) {
+    set_error("inner_join: workspace too small");
+    return DJ_ERR_WORKSPACE;
+  }
+  DJ_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
+
+  const int64_t* jbk = bk;
+  const int64_t* jbp = bp;
+  const int64_t* jpk = pk;
+  const int64_t* jpp = pp;
+
+  if (plan.bits1 == 0) {
+    set_two_offsets<<<1, 1, 0, stream>>>(boff, nb, poff, np);
+    DJ_LAUNCH_CHECK();
+  } else {
+    const size_t pw = plan.bits2 ? (pass_workspace_bytes(F1, F2) > pass_workspace_bytes(1, F1)
+                                      ? pass_workspace_bytes(F1, F2)
+                                      : pass_workspace_bytes(1, F1))
+                                 : pass_workspace_bytes(1, F1);
+    char* pass_ws_b = arena.take<char>(pw);
+    char* pass_ws_p = arena.take<char>(pw);
+    int64_t* b1k    = arena.take<int64_t>((size_t)nb);
+    int64_t* b1p    = arena.take<int64_t>((size_t)nb);
+    int64_t* p1k    = arena.take<int64_t>((size_t)np);
+    int64_t* p1p    = arena.take<int64_t>((size_t)np);
+    int64_t* boff1  = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : boff;
+    int64_t* poff1  = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : poff;
+    if (!pass_ws_b || !pass_ws_p || !b1k || !b1p || !p1k || !p1p || !boff1 || !poff1) {
+      set_error("inner_join: workspace too small");
+      return DJ_ERR_WORKSPACE;
+    }
+    PassDesc d1{1, 0, 0, 32 - plan.bits1, F1, 1, 1};
+    PassBuffers pb{};
+    pb.in_key = bk; pb.in_pay[0] = bp; pb.out_key = b1k; pb.out_pay[0] = b1p;
+    pb.nrows = nb; pb.d_parent_off = nullptr; pb.d_child_off = boff1;
+    int rc = run_partition_pass(d1, pb, pass_ws_b, pw, stream);
+    if (rc) return rc;
+    pb.in_key = pk; pb.in_pay[0] = pp; pb.out_key = p1k; pb.out_pay[0] = p1p;
+    pb.nrows = np; pb.d_child_off = poff1;
+    rc = run_partition_pass(d1, pb, pass_ws_p, pw, stream);
+    if (rc) return rc;
+    jbk = b1k; jbp = b1p; jpk = p1k; jpp = p1p;
+
+    if (plan.bits2) {
+      int64_t* b2k = arena.take<int64_t>((size_t)nb);
+      int64_t* b2p = arena.take<int64_t>((size_t)nb);
+      int64_t* p2k = arena.take<int64_t>((size_t)np);
+      int64_t* p2p = arena.take<int64_t>((size_t)np);
+      if (!b2k || !b2p || !p2k || !p2p) {
+        set_error("inner_join: workspace too small");
+        return DJ_ERR_WORKSPACE;
+      }
+      PassDesc d2{1, 0, 0, 32 - plan.bits1 - plan.bits2, F2, F1, 1};
+      pb.in_key = b1k; pb.in_pay[0] = b1p; pb.out_key = b2k; pb.out_pay[0] = b2p;
+      pb.nrows = nb; pb.d_parent_off = boff1; pb.d_child_off = boff;
+      rc = run_partition_pass(d2, pb, pass_ws_b, pw, stream);
+      if (rc) return rc;
+      pb.in_key = p1k; pb.in_pay[0] = p1p; pb.out_key = p2k; pb.out_pay[0] = p2p;
+      pb.nrows = np; pb.d_parent_off = poff1; pb.d_child_off = poff;
+      rc = run_partition_pass(d2, pb, pass_ws_p, pw, stream);
+      if (rc) return rc;
+      jbk = b2k; jbp = b2p; jpk = p2k; jpp = p2p;
+    }
+  }
+
+  JoinBuffers jb{};
+  jb.bk = jbk; jb.bp = jbp; jb.d_build_off = boff;
+  jb.pk = jpk; jb.pp = jpp; jb.d_probe_off = poff;
+  jb.nbuckets = plan.nbuckets;
+  for (int c = 0; c < 4; c++) jb.out[c] = out[c];
+  jb.out_capacity   = out_capacity;
+  jb.d_out_count    = d_out_count;
+  jb.d_work_counter = work_counter;
+  return run_bucket_join(jb, swap, stream);
+}
+
+size_t local_join_workspace(int64_t nb, int64_t np) { return local_join_ws_bytes(nb, np); }
+
+}  // namespace dj
+
+using namespace dj;
+
+extern "C" int dj_version(void) { return DJ_VERSION; }
+extern "C" const char* dj_last_error(void) { return dj::g_error; }
+extern "C" int64_t dj_kernel_launch_count(void) { return dj::g_launches.load(); }
+
+extern "C" size_t dj_hash_partition_workspace_bytes(int64_t nrows, int nparts)
+{
+  (void)nrows;
+  if (nparts < 1) nparts = 1;
+  return pass_workspace_bytes(1, nparts) + 4096;
+}
+
+extern "C" int dj_hash_partition_i64(const int64_t* d_key, const int64_t* const* h_payload_cols,
+                                     int npayload, int64_t nrows, int nparts, uint32_t seed,
+                                     int hash_id, int64_t* d_out_key,
+                                     int64_t* const* h_out_payload_cols, int64_t* d_offsets,
+                                     void* d_workspace, size_t workspace_bytes, void* stream)
+{
+  DJ_REQUIRE(nparts >= 1 && nparts <= kMaxFanout, "hash_partition: nparts %d not in [1, %d]", nparts,
+             kMaxFanout);
+  DJ_REQUIRE(npayload >= 1 && npayload <= kMaxPayload,
+             "hash_partition: %d payload columns (supported: 1..%d)", npayload, kMaxPayload);
+  DJ_REQUIRE(hash_id == DJ_HASH_MURMUR3 || hash_id == DJ_HASH_IDENTITY, "hash_partition: bad hash id");
+  DJ_REQUIRE(nrows >= 0 && d_offsets && d_workspace, "hash_partition: bad argument");
+  PassDesc desc{0, seed, hash_id, 0, nparts, 1, npayload};
+  PassBuffers buf{};
+  buf.in_key  = d_key;
+  buf.out_key = d_out_key;
+  for (int c = 0; c < npayload; c++) {
+    buf.in_pay[c]  = h_payload_cols[c];
+    buf.out_pay[c] = h_out_payload_cols[c];
+  }
+  buf.nrows        = nrows;
+  buf.d_parent_off = nullptr;
+  buf.d_child_off  = d_offsets;
+  return run_partition_pass(desc, buf, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t dj_inner_join_workspace_bytes(int64_t nbuild, int64_t nprobe)
+{
+  return local_join_ws_bytes(nbuild, nprobe);
+}
+
+extern "C" int dj_inner_join_i64(const int64_t* d_build_key, const int64_t* d_build_payload,
+                                 int64_t nbuild, const int64_t* d_probe_key,
+                                 const int64_t* d_probe_payload, int64_t nprobe,
+                                 int64_t* d_out_build_key, int64_t* d_out_build_payload,
+                                 int64_t* d_out_probe_key, int64_t* d_out_probe_payload,
+                                 int64_t out_capacity, int64_t* d_out_count, void* d_workspace,
+                                 size_t workspace_bytes, void* stream)
+{
+  DJ_REQUIRE(nbuild >= 0 && nprobe >= 0 && out_capacity >= 0 && d_out_count, "inner_join: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DJ_CUDA_TRY(cudaMemsetAsync(d_out_count, 0, sizeof(int64_t), st));
+  if (nbuild == 0 || nprobe == 0) return DJ_OK;
+  DJ_REQUIRE(d_workspace, "inner_join: workspace missing");
+  Arena arena(d_workspace, workspace_bytes);
+  int64_t* out[4] = {d_out_build_key, d_out_build_payload, d_out_probe_key, d_out_probe_payload};
+  return local_join(d_build_key, d_build_payload, nbuild, d_probe_key, d_probe_payload, nprobe, out,
+                    out_capacity, d_out_count, false, arena, st);
+}

@@ -1,0 +1,502 @@
+// comm.cu -- NCCL plumbing and the distributed inner join driver (include/dj_b200.h).
+//
+// Replaces NCCLCommunicator (src/communicator.cpp:799-875), communicate_sizes
+// (src/all_to_all_comm.cpp:54-111), the table all-to-all (:126-189,307-356) and the
+// orchestration of distributed_inner_join (src/distributed_join.cpp:134-340):
+//   * no MPI: counts travel by ncclAllGather, the unique id comes from the launcher;
+//   * no staging copies: buckets are sent from / received into their final buffers;
+//   * one ncclGroup per batch covering every column of both tables;
+//   * the reference's spinning join thread + std::atomic flags (:100-132,283-322) become two
+//     CUDA streams and events: batch b+1's exchange overlaps batch b's local join;
+//   * batch results are appended into one output (no cudf::concatenate, :333-339).
+#include <nccl.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "dj_device.cuh"
+#include "dj_internal.h"
+
+struct dj_comm {
+  ncclComm_t nccl = nullptr;
+  int rank = 0, size = 1, device = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_ready     = nullptr;
+  std::vector<cudaEvent_t> ev_batch;
+  int64_t* h_pinned = nullptr;  // pinned scratch
+  int64_t* d_small  = nullptr;  // device scratch for tiny collectives
+  size_t small_elems = 0;
+};
+
+namespace dj {
+
+int local_join(const int64_t* bk, const int64_t* bp, int64_t nb, const int64_t* pk,
+               const int64_t* pp, int64_t np, int64_t* const out[4], int64_t out_capacity,
+               int64_t* d_out_count, bool swap, Arena& arena, cudaStream_t stream);
+size_t local_join_workspace(int64_t nb, int64_t np);
+
+#define DJ_NCCL_TRY(expr)                                                                     \
+  do {                                                                                        \
+    ncclResult_t _r = (expr);                                                                 \
+    if (_r != ncclSuccess) {                                                                  \
+      dj::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, ncclGetErrorString(_r));    \
+      return DJ_ERR_NCCL;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+constexpr size_t kSmallElems = 1 << 16;
+
+static int ensure_events(dj_comm* c, int n)
+{
+  while ((int)c->ev_batch.size() < n) {
+    cudaEvent_t e;
+    DJ_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_batch.push_back(e);
+  }
+  return DJ_OK;
+}
+
+}  // namespace dj
+
+using namespace dj;
+
+extern "C" int dj_comm_unique_id(void* h_id128)
+{
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  DJ_NCCL_TRY(ncclGetUniqueId(&id));
+  memcpy(h_id128, &id, sizeof(id));
+  return DJ_OK;
+}
+
+extern "C" int dj_comm_create(int rank, int size, const void* h_id128, dj_comm_t** out)
+{
+  DJ_REQUIRE(out && size >= 1 && rank >= 0 && rank < size, "comm_create: bad rank/size");
+  dj_comm* c = new dj_comm();
+  c->rank    = rank;
+  c->size    = size;
+  DJ_CUDA_TRY(cudaGetDevice(&c->device));
+  if (size > 1) {
+    DJ_REQUIRE(h_id128, "comm_create: unique id missing");
+    ncclUniqueId id;
+    memcpy(&id, h_id128, sizeof(id));
+    DJ_NCCL_TRY(ncclCommInitRank(&c->nccl, size, id, rank));
+  }
+  DJ_CUDA_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  DJ_CUDA_TRY(cudaMallocHost(&c->h_pinned, kSmallElems * sizeof(int64_t)));
+  DJ_CUDA_TRY(cudaMalloc(&c->d_small, kSmallElems * sizeof(int64_t)));
+  c->small_elems = kSmallElems;
+  *out           = c;
+  return DJ_OK;
+}
+
+extern "C" int dj_comm_destroy(dj_comm_t* c)
+{
+  if (!c) return DJ_OK;
+  cudaDeviceSynchronize();
+  if (c->nccl) ncclCommDestroy(c->nccl);
+  for (auto e : c->ev_batch) cudaEventDestroy(e);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->d_small) cudaFree(c->d_small);
+  delete c;
+  return DJ_OK;
+}
+
+extern "C" int dj_comm_rank(const dj_comm_t* c) { return c ? c->rank : 0; }
+extern "C" int dj_comm_size(const dj_comm_t* c) { return c ? c->size : 1; }
+
+extern "C" int dj_comm_allgather_i64(dj_comm_t* c, const int64_t* h_mine, int n, int64_t* h_all,
+                                     void* stream)
+{
+  DJ_REQUIRE(c && n >= 0, "allgather: bad argument");
+  if (c->size == 1) {
+    memcpy(h_all, h_mine, (size_t)n * 8);
+    return DJ_OK;
+  }
+  DJ_REQUIRE((size_t)n * (c->size + 1) <= c->small_elems, "allgather: %d values per rank is too many", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* d_send = c->d_small;
+  int64_t* d_recv = c->d_small + n;
+  memcpy(c->h_pinned, h_mine, (size_t)n * 8);
+  DJ_CUDA_TRY(cudaMemcpyAsync(d_send, c->h_pinned, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  DJ_NCCL_TRY(ncclAllGather(d_send, d_recv, (size_t)n, ncclInt64, c->nccl, st));
+  DJ_CUDA_TRY(cudaMemcpyAsync(c->h_pinned + n, d_recv, (size_t)n * c->size * 8,
+                              cudaMemcpyDeviceToHost, st));
+  DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(h_all, c->h_pinned + n, (size_t)n * c->size * 8);
+  return DJ_OK;
+}
+
+extern "C" int dj_comm_barrier(dj_comm_t* c, void* stream)
+{
+  int64_t mine = 1;
+  std::vector<int64_t> all(c ? c->size : 1);
+  if (!c || c->size == 1) return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? DJ_OK : DJ_ERR_CUDA;
+  return dj_comm_allgather_i64(c, &mine, 1, all.data(), stream);
+}
+
+extern "C" int dj_comm_group_start(dj_comm_t*)
+{
+  DJ_NCCL_TRY(ncclGroupStart());
+  return DJ_OK;
+}
+extern "C" int dj_comm_group_end(dj_comm_t*)
+{
+  DJ_NCCL_TRY(ncclGroupEnd());
+  return DJ_OK;
+}
+extern "C" int dj_comm_send(dj_comm_t* c, const void* d_buf, int64_t nbytes, int dest, void* stream)
+{
+  DJ_REQUIRE(c && c->nccl, "send: communicator has no NCCL (size 1)");
+  DJ_NCCL_TRY(ncclSend(d_buf, (size_t)nbytes, ncclInt8, dest, c->nccl, (cudaStream_t)stream));
+  return DJ_OK;
+}
+extern "C" int dj_comm_recv(dj_comm_t* c, void* d_buf, int64_t nbytes, int source, void* stream)
+{
+  DJ_REQUIRE(c && c->nccl, "recv: communicator has no NCCL (size 1)");
+  DJ_NCCL_TRY(ncclRecv(d_buf, (size_t)nbytes, ncclInt8, source, c->nccl, (cudaStream_t)stream));
+  return DJ_OK;
+}
+
+extern "C" int dj_all_to_all(dj_comm_t* c, int group_size, const int* h_group_ranks, int self_idx,
+                             const void* const* h_send_cols, void* const* h_recv_cols,
+                             const int64_t* h_send_offsets, const int64_t* h_recv_offsets,
+                             const int* h_elem_sizes, int ncols, int include_self, void* stream)
+{
+  DJ_REQUIRE(c && group_size >= 1 && self_idx >= 0 && self_idx < group_size && ncols >= 0,
+             "all_to_all: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (include_self) {
+    const int64_t n = h_send_offsets[self_idx + 1] - h_send_offsets[self_idx];
+    DJ_REQUIRE(n == h_recv_offsets[self_idx + 1] - h_recv_offsets[self_idx],
+               "all_to_all: self send/recv sizes differ");
+    for (int col = 0; col < ncols && n > 0; col++) {
+      const size_t es = (size_t)h_elem_sizes[col];
+      DJ_CUDA_TRY(cudaMemcpyAsync((char*)h_recv_cols[col] + h_recv_offsets[self_idx] * es,
+                                  (const char*)h_send_cols[col] + h_send_offsets[self_idx] * es,
+                                  (size_t)n * es, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (group_size == 1) return DJ_OK;
+  DJ_REQUIRE(c->nccl, "all_to_all: communicator has no NCCL (size 1)");
+  DJ_NCCL_TRY(ncclGroupStart());
+  for (int col = 0; col < ncols; col++) {
+    const size_t es = (size_t)h_elem_sizes[col];
+    for (int i = 0; i < group_size; i++) {
+      if (i == self_idx) continue;
+      const int64_t ns = h_send_offsets[i + 1] - h_send_offsets[i];
+      const int64_t nr = h_recv_offsets[i + 1] - h_recv_offsets[i];
+      if (ns > 0)
+        DJ_NCCL_TRY(ncclSend((const char*)h_send_cols[col] + h_send_offsets[i] * es, (size_t)ns * es,
+                             ncclInt8, h_group_ranks[i], c->nccl, st));
+      if (nr > 0)
+        DJ_NCCL_TRY(ncclRecv((char*)h_recv_cols[col] + h_recv_offsets[i] * es, (size_t)nr * es,
+                             ncclInt8, h_group_ranks[i], c->nccl, st));
+    }
+  }
+  DJ_NCCL_TRY(ncclGroupEnd());
+  return DJ_OK;
+}
+
+// ------------------------------------------------------------------------- distributed join
+
+static const uint32_t kNvlinkSeed = 12345678u;  // src/distributed_join.cpp:211
+
+static size_t dist_ws_bytes(int64_t nl, int64_t nr, int world, int odf, double slack)
+{
+  if (world <= 1) return local_join_workspace(nl < nr ? nl : nr, nl < nr ? nr : nl) + 8192;
+  const int nparts = world * odf;
+  size_t total     = 1 << 16;
+  // partitioned copies of both tables
+  total += 2 * (align_up((size_t)nl * 8, 256) + align_up((size_t)nr * 8, 256));
+  total += 2 * pass_workspace_bytes(1, nparts) + 2 * align_up(((size_t)nparts + 1) * 8, 256);
+  // receive buffers (balanced estimate with slack)
+  const size_t rl = (size_t)((double)nl * slack) + 4096, rr = (size_t)((double)nr * slack) + 4096;
+  total += 2 * (align_up(rl * 8, 256) + align_up(rr * 8, 256)) + (size_t)odf * 4 * 256;
+  // join scratch for the largest batch
+  const size_t bl = rl / odf + 4096, br = rr / odf + 4096;
+  total += local_join_workspace((int64_t)(bl < br ? bl : br), (int64_t)(bl < br ? br : bl));
+  return total + 8192;
+}
+
+extern "C" size_t dj_distributed_inner_join_workspace_bytes(int64_t nleft, int64_t nright, int world,
+                                                            int over_decom_factor)
+{
+  return dist_ws_bytes(nleft, nright, world, over_decom_factor < 1 ? 1 : over_decom_factor, 1.15);
+}
+
+static double ms_since(std::chrono::high_resolution_clock::time_point t0)
+{
+  return std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+}
+
+extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_left_key,
+                                             const int64_t* d_left_payload, int64_t nleft,
+                                             const int64_t* d_right_key,
+                                             const int64_t* d_right_payload, int64_t nright,
+                                             int64_t* d_out_lk, int64_t* d_out_lp,
+                                             int64_t* d_out_rk, int64_t* d_out_rp,
+                                             int64_t out_capacity, int64_t* h_out_count,
+                                             dj_join_options* opts, void* d_workspace,
+                                             size_t workspace_bytes, void* stream)
+{
+  DJ_REQUIRE(nleft >= 0 && nright >= 0 && h_out_count && d_workspace, "distributed_inner_join: bad argument");
+  cudaStream_t st   = (cudaStream_t)stream;
+  const int world   = comm ? comm->size : 1;
+  const int rank    = comm ? comm->rank : 0;
+  const int odf     = (opts && opts->over_decom_factor > 1) ? opts->over_decom_factor : 1;
+  const bool timing = opts && opts->report_timing;
+  if (opts) {
+    opts->t_partition_ms = opts->t_comm_ms = opts->t_join_ms = 0;
+    opts->bytes_sent = 0;
+  }
+  Arena arena(d_workspace, workspace_bytes);
+  int64_t* d_count = arena.take<int64_t>(32);
+  DJ_REQUIRE(d_count, "distributed_inner_join: workspace too small");
+  DJ_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+  int64_t* out[4] = {d_out_lk, d_out_lp, d_out_rk, d_out_rp};
+  auto t0         = std::chrono::high_resolution_clock::now();
+
+  if (world == 1) {
+    // src/distributed_join.cpp:186-199 -- one rank: the local join is the whole job.
+    const bool swap = nright < nleft;  // build on the smaller table
+    int rc = swap ? local_join(d_right_key, d_right_payload, nright, d_left_key, d_left_payload,
+                               nleft, out, out_capacity, d_count, true, arena, st)
+                  : local_join(d_left_key, d_left_payload, nleft, d_right_key, d_right_payload,
+                               nright, out, out_capacity, d_count, false, arena, st);
+    if (rc) return rc;
+    DJ_CUDA_TRY(cudaMemcpyAsync(comm ? comm->h_pinned : h_out_count, d_count, 8,
+                                cudaMemcpyDeviceToHost, st));
+    DJ_CUDA_TRY(cudaStreamSynchronize(st));
+    if (comm) *h_out_count = comm->h_pinned[0];
+    if (timing) {
+      opts->t_join_ms = ms_since(t0);
+      // the reference labels this branch's time "Hash partition" (src/distributed_join.cpp:194)
+      printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_join_ms);
+    }
+    return *h_out_count > out_capacity ? (set_error("join output needs %lld rows, capacity %lld",
+                                                    (long long)*h_out_count, (long long)out_capacity),
+                                          DJ_ERR_OVERFLOW)
+                                       : DJ_OK;
+  }
+
+  const int G      = world;  // one NVSwitch box: the NVLink group is every rank
+  const int nparts = G * odf;
+  DJ_REQUIRE(nparts <= kMaxFanout, "distributed_inner_join: %d partitions exceed %d", nparts, kMaxFanout);
+  int rc = ensure_events(comm, odf);
+  if (rc) return rc;
+
+  // ---- 1. hash partition both tables into G*odf buckets (src/distributed_join.cpp:213-225)
+  const size_t pw  = pass_workspace_bytes(1, nparts);
+  char* pws_l      = arena.take<char>(pw);
+  char* pws_r      = arena.take<char>(pw);
+  int64_t* plk     = arena.take<int64_t>((size_t)nleft);
+  int64_t* plp     = arena.take<int64_t>((size_t)nleft);
+  int64_t* prk     = arena.take<int64_t>((size_t)nright);
+  int64_t* prp     = arena.take<int64_t>((size_t)nright);
+  int64_t* d_off_l = arena.take<int64_t>((size_t)nparts + 1);
+  int64_t* d_off_r = arena.take<int64_t>((size_t)nparts + 1);
+  if (!pws_l || !pws_r || !plk || !plp || !prk || !prp || !d_off_l || !d_off_r) {
+    set_error("distributed_inner_join: workspace too small for the partitioned tables");
+    return DJ_ERR_WORKSPACE;
+  }
+  PassDesc desc{0, kNvlinkSeed, DJ_HASH_MURMUR3, 0, nparts, 1, 1};
+  PassBuffers pb{};
+  pb.in_key = d_left_key; pb.in_pay[0] = d_left_payload; pb.out_key = plk; pb.out_pay[0] = plp;
+  pb.nrows = nleft; pb.d_child_off = d_off_l;
+  rc = run_partition_pass(desc, pb, pws_l, pw, st);
+  if (rc) return rc;
+  pb.in_key = d_right_key; pb.in_pay[0] = d_right_payload; pb.out_key = prk; pb.out_pay[0] = prp;
+  pb.nrows = nright; pb.d_child_off = d_off_r;
+  rc = run_partition_pass(desc, pb, pws_r, pw, st);
+  if (rc) return rc;
+
+  // ---- 2. sizes: offsets to the host, counts all-gathered over NCCL (communicate_sizes)
+  std::vector<int64_t> off_l(nparts + 1), off_r(nparts + 1);
+  int64_t* hp = comm->h_pinned + 4096;
+  DJ_CUDA_TRY(cudaMemcpyAsync(hp, d_off_l, (size_t)(nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
+  DJ_CUDA_TRY(cudaMemcpyAsync(hp + nparts + 1, d_off_r, (size_t)(nparts + 1) * 8,
+                              cudaMemcpyDeviceToHost, st));
+  DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(off_l.data(), hp, (size_t)(nparts + 1) * 8);
+  memcpy(off_r.data(), hp + nparts + 1, (size_t)(nparts + 1) * 8);
+  if (timing) {
+    opts->t_partition_ms = ms_since(t0);
+    printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
+  }
+
+  // mine[t*nparts + q] = rows of my table t in bucket q; plus my workspace size for a
+  // collective fits-check
+  std::vector<int64_t> mine(2 * nparts + 1), all((size_t)world * (2 * nparts + 1));
+  for (int q = 0; q < nparts; q++) {
+    mine[q]          = off_l[q + 1] - off_l[q];
+    mine[nparts + q] = off_r[q + 1] - off_r[q];
+  }
+  mine[2 * nparts] = (int64_t)workspace_bytes;
+  rc = dj_comm_allgather_i64(comm, mine.data(), 2 * nparts + 1, all.data(), st);
+  if (rc) return rc;
+  auto cnt = [&](int src, int table, int q) { return all[(size_t)src * (2 * nparts + 1) + table * nparts + q]; };
+
+  // ---- 3. receive layout per batch (allocate_communicated_table, src/all_to_all_comm.cpp:701-729)
+  struct Batch {
+    std::vector<int64_t> recv_off[2];
+    int64_t* key[2];
+    int64_t* pay[2];
+  };
+  std::vector<Batch> batches(odf);
+  bool fits_everywhere = true;
+  for (int r = 0; r < world; r++) {
+    // every rank evaluates every rank's need so that a too-small workspace fails collectively
+    size_t need = arena.used;  // same prefix layout on every rank up to table sizes; estimate
+    size_t recv_total[2] = {0, 0};
+    size_t max_b[2]      = {0, 0};
+    for (int b = 0; b < odf; b++)
+      for (int t = 0; t < 2; t++) {
+        size_t rows = 0;
+        for (int s = 0; s < world; s++) rows += (size_t)cnt(s, t, b * G + r);
+        recv_total[t] += rows;
+        if (rows > max_b[t]) max_b[t] = rows;
+      }
+    if (r == rank) {
+      need += 2 * (align_up(recv_total[0] * 8, 256) + align_up(recv_total[1] * 8, 256)) +
+              (size_t)odf * 4 * 256;
+      need += local_join_workspace((int64_t)(max_b[0] < max_b[1] ? max_b[0] : max_b[1]),
+                                   (int64_t)(max_b[0] < max_b[1] ? max_b[1] : max_b[0]));
+      if (need > workspace_bytes) fits_everywhere = false;
+    }
+  }
+  // agree on the verdict (one more tiny all-gather keeps every rank in step)
+  {
+    int64_t ok = fits_everywhere ? 1 : 0;
+    std::vector<int64_t> oks(world);
+    rc = dj_comm_allgather_i64(comm, &ok, 1, oks.data(), st);
+    if (rc) return rc;
+    for (int r = 0; r < world; r++)
+      if (!oks[r]) {
+        set_error("distributed_inner_join: workspace too small on rank %d for its received partitions", r);
+        return DJ_ERR_WORKSPACE;
+      }
+  }
+  for (int b = 0; b < odf; b++) {
+    for (int t = 0; t < 2; t++) {
+      auto& ro = batches[b].recv_off[t];
+      ro.assign(G + 1, 0);
+      for (int s = 0; s < G; s++) ro[s + 1] = ro[s] + cnt(s, t, b * G + rank);
+      batches[b].key[t] = arena.take<int64_t>((size_t)ro[G]);
+      batches[b].pay[t] = arena.take<int64_t>((size_t)ro[G]);
+      if (!batches[b].key[t] || !batches[b].pay[t]) {
+        set_error("distributed_inner_join: workspace too small for receive buffers");
+        return DJ_ERR_WORKSPACE;
+      }
+    }
+  }
+
+  // ---- 4. per batch: one grouped exchange on the comm stream, local join on the caller's
+  //         stream; batch b+1's exchange overlaps batch b's join.
+  std::vector<int> group_ranks(G);
+  for (int i = 0; i < G; i++) group_ranks[i] = i;
+  DJ_CUDA_TRY(cudaEventRecord(comm->ev_ready, st));
+  DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_ready, 0));
+  const size_t join_mark = arena.used;
+  for (int b = 0; b < odf; b++) {
+    auto tb = std::chrono::high_resolution_clock::now();
+    const int64_t* send_off[2] = {off_l.data() + (size_t)b * G, off_r.data() + (size_t)b * G};
+    const void* send_cols[4]   = {plk, plp, prk, prp};
+    void* recv_cols[4] = {batches[b].key[0], batches[b].pay[0], batches[b].key[1], batches[b].pay[1]};
+    const int es[2]    = {8, 8};
+    // self partition first (explicit copy, src/all_to_all_comm.cpp:610-653), then the wire
+    DJ_NCCL_TRY(ncclGroupStart());
+    for (int t = 0; t < 2; t++) {
+      rc = dj_all_to_all(comm, G, group_ranks.data(), rank, send_cols + 2 * t, recv_cols + 2 * t,
+                         send_off[t], batches[b].recv_off[t].data(), es, 2, 1, comm->comm_stream);
+      if (rc) return rc;
+      if (opts)
+        for (int i = 0; i < G; i++)
+          if (i != rank) opts->bytes_sent += 16 * (send_off[t][i + 1] - send_off[t][i]);
+    }
+    DJ_NCCL_TRY(ncclGroupEnd());
+    DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[b], comm->comm_stream));
+    if (timing) {
+      DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
+      double ms = ms_since(tb);
+      opts->t_comm_ms += ms;
+      printf("Rank %d: All-to-all communication on batch %d takes %.0fms\n", rank, b, ms);
+    }
+    DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_batch[b], 0));
+    auto tj = std::chrono::high_resolution_clock::now();
+    const int64_t nl = batches[b].recv_off[0][G], nr = batches[b].recv_off[1][G];
+    arena.used       = join_mark;  // join scratch is reused batch after batch (same stream)
+    const bool swap  = nr < nl;
+    rc = swap ? local_join(batches[b].key[1], batches[b].pay[1], nr, batches[b].key[0],
+                           batches[b].pay[0], nl, out, out_capacity, d_count, true, arena, st)
+              : local_join(batches[b].key[0], batches[b].pay[0], nl, batches[b].key[1],
+                           batches[b].pay[1], nr, out, out_capacity, d_count, false, arena, st);
+    if (rc) return rc;
+    if (timing) {
+      DJ_CUDA_TRY(cudaStreamSynchronize(st));
+      double ms = ms_since(tj);
+      opts->t_join_ms += ms;
+      printf("Rank %d: Local join on batch %d takes %.0fms\n", rank, b, ms);
+    }
+  }
+  DJ_CUDA_TRY(cudaMemcpyAsync(comm->h_pinned, d_count, 8, cudaMemcpyDeviceToHost, st));
+  DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
+  *h_out_count = comm->h_pinned[0];
+  if (*h_out_count > out_capacity) {
+    set_error("join output needs %lld rows, capacity %lld", (long long)*h_out_count, (long long)out_capacity);
+    return DJ_ERR_OVERFLOW;
+  }
+  return DJ_OK;
+}
+
+extern "C" size_t dj_distributed_inner_join_host_workspace_bytes(int64_t nleft, int64_t nright,
+                                                                 int64_t out_capacity, int world,
+                                                                 int over_decom_factor)
+{
+  return dj_distributed_inner_join_workspace_bytes(nleft, nright, world, over_decom_factor) +
+         2 * (align_up((size_t)nleft * 8, 256) + align_up((size_t)nright * 8, 256)) +
+         4 * align_up((size_t)out_capacity * 8, 256) + 8192;
+}
+
+extern "C" int dj_distributed_inner_join_i64_host(
+  dj_comm_t* comm, const int64_t* h_left_key, const int64_t* h_left_payload, int64_t nleft,
+  const int64_t* h_right_key, const int64_t* h_right_payload, int64_t nright, int64_t* h_out_lk,
+  int64_t* h_out_lp, int64_t* h_out_rk, int64_t* h_out_rp, int64_t out_capacity,
+  int64_t* h_out_count, dj_join_options* opts, void* d_workspace, size_t workspace_bytes,
+  void* stream)
+{
+  DJ_REQUIRE(d_workspace && h_out_count, "distributed_inner_join_host: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena arena(d_workspace, workspace_bytes);
+  int64_t* dlk = arena.take<int64_t>((size_t)nleft);
+  int64_t* dlp = arena.take<int64_t>((size_t)nleft);
+  int64_t* drk = arena.take<int64_t>((size_t)nright);
+  int64_t* drp = arena.take<int64_t>((size_t)nright);
+  int64_t* o[4];
+  for (int c = 0; c < 4; c++) o[c] = arena.take<int64_t>((size_t)out_capacity);
+  if (!dlk || !dlp || !drk || !drp || !o[0] || !o[1] || !o[2] || !o[3]) {
+    set_error("distributed_inner_join_host: workspace too small");
+    return DJ_ERR_WORKSPACE;
+  }
+  DJ_CUDA_TRY(cudaMemcpyAsync(dlk, h_left_key, (size_t)nleft * 8, cudaMemcpyHostToDevice, st));
+  DJ_CUDA_TRY(cudaMemcpyAsync(dlp, h_left_payload, (size_t)nleft * 8, cudaMemcpyHostToDevice, st));
+  DJ_CUDA_TRY(cudaMemcpyAsync(drk, h_right_key, (size_t)nright * 8, cudaMemcpyHostToDevice, st));
+  DJ_CUDA_TRY(cudaMemcpyAsync(drp, h_right_payload, (size_t)nright * 8, cudaMemcpyHostToDevice, st));
+  const size_t off = align_up(arena.used, 256);
+  int rc = dj_distributed_inner_join_i64(comm, dlk, dlp, nleft, drk, drp, nright, o[0], o[1], o[2],
+                                         o[3], out_capacity, h_out_count, opts,
+                                         (char*)d_workspace + off, workspace_bytes - off, stream);
+  if (rc && rc != DJ_ERR_OVERFLOW) return rc;
+  const int64_t n = *h_out_count < out_capacity ? *h_out_count : out_capacity;
+  int64_t* h[4]   = {h_out_lk, h_out_lp, h_out_rk, h_out_rp};
+  for (int c = 0; c < 4; c++)
+    DJ_CUDA_TRY(cudaMemcpyAsync(h[c], o[c], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  return rc;
+}
