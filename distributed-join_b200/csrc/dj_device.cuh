@@ -151,9 +151,10 @@ __host__ __device__ __forceinline__ uint64_t feistel_perm(uint64_t x, uint64_t L
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- block-wide exclusive scan
 // Exclusive prefix sum of one int per thread across a THREADS-wide CTA.  `warp_sums` is
-// THREADS/32 ints of shared memory.  Contains two __syncthreads.
+// 33 ints of shared memory; warp_sums[32] receives the block total.  Contains two
+// __syncthreads (callers must sync again before reusing warp_sums).
 template <int THREADS>
-__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total = nullptr)
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = v;
@@ -173,7 +174,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
       if (lane >= d) wi += t;
     }
     if (lane < THREADS / 32) warp_sums[lane] = wi - w;  // exclusive warp offsets
-    if (total && lane == 31) *total = wi;
+    if (lane == 31) warp_sums[32] = wi;
   }
   __syncthreads();
   return warp_sums[warp] + incl - v;

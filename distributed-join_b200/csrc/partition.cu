@@ -70,7 +70,7 @@ __device__ __forceinline__ int find_parent(const int* prefix, int P, int t)
 __global__ void plan_kernel(const int64_t* parent_off_in, int64_t nrows, int P,
                             int64_t* parent_off_out, int* hist_tiles, int* scat_tiles)
 {
-  __shared__ int warp_sums[32];
+  __shared__ int warp_sums[33];
   const int tid = threadIdx.x;
   int64_t lo = 0, hi = 0;
   if (tid < P) {
@@ -84,14 +84,13 @@ __global__ void plan_kernel(const int64_t* parent_off_in, int64_t nrows, int P,
   int64_t n = hi - lo;
   int ht    = (int)((n + kHistTileRows - 1) / kHistTileRows);
   int st    = (int)((n + kScatterTile - 1) / kScatterTile);
-  int htot = 0, stot = 0;
-  int he = block_exclusive_scan<1024>(ht, warp_sums, &htot);
+  int he = block_exclusive_scan<1024>(ht, warp_sums);
   if (tid < P) hist_tiles[tid] = he;
-  if (tid == 0) hist_tiles[P] = htot;
+  if (tid == 0) hist_tiles[P] = warp_sums[32];
   __syncthreads();
-  int se = block_exclusive_scan<1024>(st, warp_sums, &stot);
+  int se = block_exclusive_scan<1024>(st, warp_sums);
   if (tid < P) scat_tiles[tid] = se;
-  if (tid == 0) scat_tiles[P] = stot;
+  if (tid == 0) scat_tiles[P] = warp_sums[32];
 }
 
 // ---------------------------------------------------------------- histogram
@@ -135,7 +134,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(PassDev d)
   int64_t* s_delta = spay + (size_t)NPAY * T;
   int* s_start     = reinterpret_cast<int*>(s_delta + d.F);
   uint16_t* sbkt   = reinterpret_cast<uint16_t*>(s_start + d.F);
-  __shared__ int warp_sums[32];
+  __shared__ int warp_sums[33];
   __shared__ int s_parent;
 
   const int tid   = threadIdx.x;
