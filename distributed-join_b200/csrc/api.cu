@@ -1,6 +1,8 @@
 // api.cu -- C ABI entry points for the single-GPU stages (include/dj_b200.h):
 // dj_hash_partition_i64 and dj_inner_join_i64, plus library bookkeeping.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 
@@ -21,6 +23,42 @@ void set_error(const char* fmt, ...)
 }
 
 void count_launch(int n) { g_launches += n; }
+
+// ---- optional per-kernel event timing
+static bool g_prof_on = false;
+struct ProfRec { int cat; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t prof_event()
+{
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int category, cudaStream_t st) : cat(category), stream(st), slot(-1)
+{
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{cat, prof_event(), prof_event()};
+  cudaEventRecord(r.a, stream);
+  g_prof_recs.push_back(r);
+  slot = (int)g_prof_recs.size() - 1;
+}
+
+ProfScope::~ProfScope()
+{
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof_recs[slot].b, stream);
+}
 
 int sm_count()
 {
@@ -166,6 +204,33 @@ using namespace dj;
 extern "C" int dj_version(void) { return DJ_VERSION; }
 extern "C" const char* dj_last_error(void) { return dj::g_error; }
 extern "C" int64_t dj_kernel_launch_count(void) { return dj::g_launches.load(); }
+
+extern "C" int dj_profile_enable(int on)
+{
+  std::lock_guard<std::mutex> lk(dj::g_prof_mu);
+  dj::g_prof_on = on != 0;
+  return DJ_OK;
+}
+
+extern "C" int dj_profile_read(double* h_ms4, int64_t* h_launches4)
+{
+  std::lock_guard<std::mutex> lk(dj::g_prof_mu);
+  for (int c = 0; c < DJ_PROF_NCAT; c++) {
+    h_ms4[c]       = 0;
+    h_launches4[c] = 0;
+  }
+  for (auto& r : dj::g_prof_recs) {
+    DJ_CUDA_TRY(cudaEventSynchronize(r.b));
+    float ms = 0;
+    DJ_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    h_ms4[r.cat] += ms;
+    h_launches4[r.cat] += 1;
+    dj::g_prof_pool.push_back(r.a);
+    dj::g_prof_pool.push_back(r.b);
+  }
+  dj::g_prof_recs.clear();
+  return DJ_OK;
+}
 
 extern "C" size_t dj_hash_partition_workspace_bytes(int64_t nrows, int nparts)
 {

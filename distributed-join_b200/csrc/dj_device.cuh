@@ -38,6 +38,15 @@ void count_launch(int n = 1);
 
 int sm_count();
 
+// Brackets one kernel launch with CUDA events when profiling is enabled (dj_profile_enable).
+struct ProfScope {
+  int cat;
+  cudaStream_t stream;
+  int slot;
+  ProfScope(int category, cudaStream_t st);
+  ~ProfScope();
+};
+
 // ---------------------------------------------------------------- hashing
 __host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r)
 {

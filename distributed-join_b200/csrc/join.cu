@@ -206,7 +206,10 @@ int run_bucket_join(const JoinBuffers& jb, bool swap_output_sides, cudaStream_t 
   if (per_sm < 1) per_sm = 1;
   int grid = sm_count() * per_sm;
   if (grid > jb.nbuckets) grid = jb.nbuckets;
-  bucket_join_kernel<<<grid, kJoinThreads, smem, stream>>>(d);
+  {
+    ProfScope prof(DJ_PROF_JOIN, stream);
+    bucket_join_kernel<<<grid, kJoinThreads, smem, stream>>>(d);
+  }
   DJ_LAUNCH_CHECK();
   return DJ_OK;
 }

@@ -248,7 +248,10 @@ int launch_scatter(const PassDev& dev, int F, cudaStream_t stream)
   int per_sm = 1;
   DJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScatterThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  kern<<<sm_count() * per_sm, kScatterThreads, smem, stream>>>(dev);
+  {
+    ProfScope prof(DJ_PROF_SCATTER, stream);
+    kern<<<sm_count() * per_sm, kScatterThreads, smem, stream>>>(dev);
+  }
   DJ_LAUNCH_CHECK();
   return DJ_OK;
 }
@@ -342,17 +345,23 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
 
   const int hist_grid = sm_count() * 4;
   const size_t hsmem  = (size_t)desc.F * sizeof(int);
-  if (desc.mode == 0)
-    hist_kernel<0><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
-  else
-    hist_kernel<1><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
+  {
+    ProfScope prof(DJ_PROF_HIST, stream);
+    if (desc.mode == 0)
+      hist_kernel<0><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
+    else
+      hist_kernel<1><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
+  }
   DJ_LAUNCH_CHECK();
 
-  DJ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, counts,
-                                            (unsigned long long*)buf.d_child_off, (int)(nb + 1),
-                                            stream));
-  count_launch(2);
-  DJ_CUDA_TRY(cudaMemcpyAsync(cursor, buf.d_child_off, nb * 8, cudaMemcpyDeviceToDevice, stream));
+  {
+    ProfScope prof(DJ_PROF_OTHER, stream);
+    DJ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, counts,
+                                              (unsigned long long*)buf.d_child_off, (int)(nb + 1),
+                                              stream));
+    count_launch(2);
+    DJ_CUDA_TRY(cudaMemcpyAsync(cursor, buf.d_child_off, nb * 8, cudaMemcpyDeviceToDevice, stream));
+  }
 
   return desc.mode == 0 ? launch_scatter_npay<0>(dev, desc.npay, desc.F, stream)
                         : launch_scatter_npay<1>(dev, desc.npay, desc.F, stream);

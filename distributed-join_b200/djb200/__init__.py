@@ -55,7 +55,8 @@ class JoinOptions(C.Structure):
 
 # every symbol include/dj_b200.h declares (checked by the CPU test-suite)
 ABI_SYMBOLS = [
-    "dj_version", "dj_last_error", "dj_kernel_launch_count", "dj_partition_ids_i64",
+    "dj_version", "dj_last_error", "dj_kernel_launch_count", "dj_profile_enable", "dj_profile_read",
+    "dj_partition_ids_i64",
     "dj_hash_partition_workspace_bytes", "dj_hash_partition_i64", "dj_inner_join_workspace_bytes",
     "dj_inner_join_i64", "dj_generate_build_bitmap", "dj_generate_rows_i64", "dj_multiset_checksum4",
     "dj_comm_unique_id", "dj_comm_create", "dj_comm_destroy", "dj_comm_rank", "dj_comm_size",
@@ -81,6 +82,8 @@ def lib() -> C.CDLL:
     L.dj_version.restype = C.c_int
     L.dj_last_error.restype = C.c_char_p
     L.dj_kernel_launch_count.restype = i64
+    L.dj_profile_enable.argtypes = [C.c_int]
+    L.dj_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
     L.dj_partition_ids_i64.argtypes = [vp, i64, u32, C.c_int, C.c_int, vp, vp]
     L.dj_hash_partition_workspace_bytes.restype = sz
     L.dj_hash_partition_workspace_bytes.argtypes = [i64, C.c_int]
@@ -138,6 +141,21 @@ def _i64dev(t: torch.Tensor) -> torch.Tensor:
 
 def kernel_launch_count() -> int:
     return int(lib().dj_kernel_launch_count())
+
+
+PROF_CATEGORIES = ("hist", "scatter", "join", "other")
+
+
+def profile_enable(on: bool):
+    _check(lib().dj_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{category: (milliseconds, launches)} since the last read (device time from CUDA events)."""
+    ms = (C.c_double * 4)()
+    n = (C.c_int64 * 4)()
+    _check(lib().dj_profile_read(ms, n))
+    return {c: (ms[i], n[i]) for i, c in enumerate(PROF_CATEGORIES)}
 
 
 def workspace(nbytes: int, device=None) -> torch.Tensor:

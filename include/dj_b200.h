@@ -49,6 +49,14 @@ const char* dj_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t dj_kernel_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, every launch of the four
+ * kernel categories is bracketed by CUDA events on its own stream.  dj_profile_read
+ * synchronises those events, returns the summed milliseconds and launch counts per category
+ * (hist, scatter, join, other) and clears the record. */
+enum { DJ_PROF_HIST = 0, DJ_PROF_SCATTER = 1, DJ_PROF_JOIN = 2, DJ_PROF_OTHER = 3, DJ_PROF_NCAT = 4 };
+int dj_profile_enable(int on);
+int dj_profile_read(double* h_ms4, int64_t* h_launches4);
+
 /* ------------------------------------------------------------------------------------
  * Hashing.  partition id = (murmur3_x86_32(key bytes, seed) + 0x9e3779b9) % nparts,
  * restating cudf::hash_partition's row hash for one int64 key column
