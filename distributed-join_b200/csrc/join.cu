@@ -2,15 +2,27 @@
 //
 // Replaces cudf::inner_join as called by local_join_helper (src/distributed_join.cpp:71-83).
 // Both tables arrive radix-partitioned (partition.cu, mode 1) into buckets whose build side
-// fits one CTA's shared-memory table.  Per bucket a CTA
-//   1. inserts the build rows into a linear-probing table (64-bit key + 64-bit payload per
-//      slot, occupancy bitmap claimed with atomicOr so no key value is reserved as "empty"),
-//   2. streams the probe rows through it, one row per lane; matches are compacted with
-//      __ballot_sync / popc into a CTA-wide staging tile in shared memory,
-//   3. flushes the staging tile with ONE global atomicAdd per flush and coalesced stores to
-//      the four output columns (so the output needs no cudf::concatenate afterwards).
+// fits one CTA's shared-memory table.  One persistent CTA per SM (31 consumer warps + 1
+// producer warp) walks a contiguous range of buckets:
+//
+//   producer warp   one elected lane streams every bucket's rows HBM -> shared memory with TMA
+//                   bulk copies (cp.async.bulk + mbarrier complete_tx): one build-chunk stage
+//                   and a ring of probe-chunk stages, refilled as soon as consumers release them,
+//                   so global-memory latency never sits on the consumers' critical path;
+//   consumer warps  1. insert the staged build rows into a linear-probing table (64-bit key +
+//                      64-bit payload per slot; occupancy bitmap claimed with atomicOr, so no key
+//                      value is reserved as "empty"; two bitmaps ping-pong so the next one is
+//                      cleared off the critical path),
+//                   2. probe one staged row per lane; matches are compacted with __ballot_sync /
+//                      popc into a shared-memory output tile,
+//                   3. flush full output tiles with ONE global atomicAdd per tile and coalesced
+//                      stores; the atomic's round trip is hidden behind the next round of probing
+//                      (three tiles rotate), and batch results land in one output so no
+//                      cudf::concatenate is needed afterwards.
 // Multimap semantics: probing continues past a hit until an empty slot.  Build buckets larger
-// than the table (skew / duplicates) are processed in chunks, re-streaming the probe side.
+// than one chunk (skew / duplicates) are processed chunk by chunk, re-streaming the probe side.
+#include <cstdlib>
+
 #include "dj_device.cuh"
 #include "dj_internal.h"
 
@@ -18,12 +30,25 @@ namespace dj {
 
 namespace {
 
-constexpr int kJoinThreads = 512;
-constexpr int kSlots       = 4096;             // table slots per CTA (power of 2)
-constexpr int kChunkRows   = kSlots * 3 / 4;   // max build rows inserted at once
-constexpr int kTargetRows  = kSlots * 3 / 8;   // planned average build rows per bucket
-constexpr int kOutCap      = 1024;             // staged output rows per CTA
-constexpr int kFlushAt     = kOutCap - kJoinThreads;
+// Compile-time shape of one CTA.  Two shapes are built: A = one 1024-thread CTA per SM for
+// ~1.5K-row buckets, B = two 512-thread CTAs per SM for ~0.75K-row buckets.
+template <int THREADS, int SLOTS, int BUILD_CHUNK, int TARGET_ROWS, int PROBE_STAGES, int OUT_ROWS>
+struct JoinCfg {
+  static constexpr int kThreads     = THREADS;
+  static constexpr int kConsumers   = THREADS - 32;
+  static constexpr int kConsWarps   = kConsumers / 32;
+  static constexpr int kSlots       = SLOTS;        // 32-bit slots per table (power of 2)
+  static constexpr int kBuildChunk  = BUILD_CHUNK;  // max build rows per table (<= 2048)
+  static constexpr int kTargetRows  = TARGET_ROWS;  // planned average build rows per bucket
+  static constexpr int kProbeChunk  = kConsumers;   // one probe row per consumer thread and round
+  static constexpr int kProbeStages = PROBE_STAGES;
+  static constexpr int kOutRows     = OUT_ROWS;     // rows per output tile
+};
+using CfgA = JoinCfg<1024, 8192, 1792, 1536, 2, 576>;
+using CfgB = JoinCfg<512, 4096, 1024, 768, 2, 256>;
+
+constexpr int kOutTiles    = 3;    // filling / atomicAdd in flight / draining
+constexpr int kDescBuckets = 128;  // bucket descriptors cached per refill
 
 struct JoinDev {
   const int64_t* bk;
@@ -36,141 +61,357 @@ struct JoinDev {
   int64_t* out[4];
   int64_t out_capacity;
   unsigned long long* out_count;
-  int* work_counter;
 };
 
-struct __align__(16) JoinSmem {
-  int64_t skey[kSlots];
-  int64_t spay[kSlots];
-  int64_t sout[4][kOutCap];
-  unsigned occ[kSlots / 32];
-  int scnt;
-  int sbucket;
-  unsigned long long sbase;
+template <class C>
+struct __align__(128) JoinSmem {
+  uint32_t slots[2][C::kSlots];
+  int64_t bkey[2][C::kBuildChunk + 2];
+  int64_t bpay[2][C::kBuildChunk + 2];
+  int64_t pkey[C::kProbeStages][C::kProbeChunk + 2];
+  int64_t ppay[C::kProbeStages][C::kProbeChunk + 2];
+  int64_t sout[kOutTiles][4][C::kOutRows];
+  int64_t dboff[kDescBuckets + 1];
+  int64_t dpoff[kDescBuckets + 1];
+  unsigned long long full_build[2], empty_build[2];
+  unsigned long long full_probe[C::kProbeStages], empty_probe[C::kProbeStages];
+  unsigned long long sbase[kOutTiles];
+  int scnt[kOutTiles];
 };
 
-__device__ __forceinline__ void flush_staging(JoinSmem& s, const JoinDev& d, int n)
+// ---------------------------------------------------------------- PTX helpers (mbarrier + TMA)
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
-  // all threads call; n is uniform
-  if (n > kOutCap) n = kOutCap;
-  if (threadIdx.x == 0) s.sbase = atomicAdd(d.out_count, (unsigned long long)n);
-  __syncthreads();
-  const int64_t base = (int64_t)s.sbase;
-#pragma unroll
-  for (int c = 0; c < 4; c++)
-    for (int i = threadIdx.x; i < n; i += kJoinThreads)
-      if (base + i < d.out_capacity) d.out[c][base + i] = s.sout[c][i];
-  __syncthreads();
-  if (threadIdx.x == 0) s.scnt = 0;
-  __syncthreads();
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_LOOP:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra WAIT_DONE;\n"
+    "bra WAIT_LOOP;\n"
+    "WAIT_DONE:\n"
+    "}\n" ::"r"(smem_u32(bar)),
+    "r"(parity)
+    : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         unsigned long long* bar)
+{
+  asm volatile(
+    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+      smem_u32(smem_dst)),
+    "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+    : "memory");
+}
+template <int N>
+__device__ __forceinline__ void consumer_sync()
+{
+  asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
 }
 
-__global__ void __launch_bounds__(kJoinThreads, 2) bucket_join_kernel(JoinDev d)
+// 16-byte aligned window covering n int64 starting at p
+struct Window {
+  const char* base;
+  uint32_t bytes;
+};
+__device__ __forceinline__ Window window_of(const int64_t* p, int n)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  JoinSmem& s    = *reinterpret_cast<JoinSmem*>(smem_raw);
+  const uintptr_t a  = reinterpret_cast<uintptr_t>(p);
+  const uintptr_t lo = a & ~(uintptr_t)15;
+  const uintptr_t hi = (a + (uintptr_t)n * 8 + 15) & ~(uintptr_t)15;
+  return Window{reinterpret_cast<const char*>(lo), (uint32_t)(hi - lo)};
+}
+__device__ __forceinline__ int skip_of(const int64_t* p)
+{
+  return (int)((reinterpret_cast<uintptr_t>(p) & 15) >> 3);
+}
+
+// Build jobs of the cached descriptor block: (bucket, build chunk) pairs whose bucket is
+// non-empty on both sides.  Every thread walks them identically.
+template <class S>
+__device__ __forceinline__ int next_valid_bucket(const S& s, int lb, int nd)
+{
+  while (lb < nd && (s.dboff[lb + 1] == s.dboff[lb] || s.dpoff[lb + 1] == s.dpoff[lb])) lb++;
+  return lb;
+}
+
+// Slot word: bit 31 = occupied, bits 30..11 = 20-bit key fingerprint, bits 10..0 = build row.
+__device__ __forceinline__ uint32_t slot_tag(uint32_t h) { return 0x100000u | (h >> 12); }
+
+template <class C>
+__global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
+{
+  using Smem = JoinSmem<C>;
+  constexpr int kConsumers = C::kConsumers;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& s        = *reinterpret_cast<Smem*>(smem_raw);
   const int tid  = threadIdx.x;
   const int lane = tid & 31;
-  if (tid == 0) s.scnt = 0;
+  const int warp = tid >> 5;
+  const bool is_producer = warp == C::kConsWarps;
 
-  while (true) {
+  if (tid == 0) {
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&s.full_build[i], 1);
+      mbar_init(&s.empty_build[i], C::kConsWarps);
+    }
+    for (int i = 0; i < C::kProbeStages; i++) {
+      mbar_init(&s.full_probe[i], 1);
+      mbar_init(&s.empty_probe[i], C::kConsWarps);
+    }
+    for (int i = 0; i < kOutTiles; i++) s.scnt[i] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 2 * C::kSlots; i += C::kThreads) (&s.slots[0][0])[i] = 0;
+  __syncthreads();
+
+  // contiguous bucket range of this CTA
+  const int lo = (int)((int64_t)d.nbuckets * blockIdx.x / gridDim.x);
+  const int hi = (int)((int64_t)d.nbuckets * (blockIdx.x + 1) / gridDim.x);
+
+  uint32_t q = 0;  // probe-job ordinal (stage = q % kProbeStages)
+  uint32_t u = 0;  // build-job ordinal (stage = table = u & 1)
+  // Output tiles rotate filling -> pending (its atomicAdd is in flight during the next build
+  // job) -> draining (copied out while a third tile already fills) -> free.
+  int cur = 0, pend_tile = 0, pend_n = 0;
+  unsigned long long pend_base_reg = 0;  // thread 0 only
+
+  for (int base = lo; base < hi; base += kDescBuckets) {
+    const int nd = min(kDescBuckets, hi - base);
+    __syncthreads();  // everyone is done with the previous descriptors
+    for (int i = tid; i <= nd; i += C::kThreads) {
+      s.dboff[i] = d.boff[base + i];
+      s.dpoff[i] = d.poff[base + i];
+    }
     __syncthreads();
-    if (tid == 0) s.sbucket = atomicAdd(d.work_counter, 1);
-    __syncthreads();
-    const int b = s.sbucket;
-    if (b >= d.nbuckets) break;
-    const int64_t b0 = d.boff[b], b1 = d.boff[b + 1];
-    const int64_t p0 = d.poff[b], p1 = d.poff[b + 1];
-    if (b1 == b0 || p1 == p0) continue;
 
-    for (int64_t c0 = b0; c0 < b1; c0 += kChunkRows) {
-      const int64_t c1 = (c0 + kChunkRows < b1) ? c0 + kChunkRows : b1;
-      if (tid < kSlots / 32) s.occ[tid] = 0;
-      __syncthreads();
-
-      // ---- build: claim a slot bit, then fill the slot
-      for (int64_t i = c0 + tid; i < c1; i += kJoinThreads) {
-        const int64_t k = d.bk[i];
-        const int64_t v = d.bp[i];
-        uint32_t slot   = slot_hash_i64(k) & (kSlots - 1);
-        while (true) {
-          const unsigned bit = 1u << (slot & 31);
-          const unsigned old = atomicOr(&s.occ[slot >> 5], bit);
-          if (!(old & bit)) break;
-          slot = (slot + 1) & (kSlots - 1);
-        }
-        s.skey[slot] = k;
-        s.spay[slot] = v;
-      }
-      __syncthreads();
-
-      // ---- probe: one row per lane and round, warp-synchronous chain walk
-      for (int64_t r0 = p0; r0 < p1; r0 += kJoinThreads) {
-        const int64_t i = r0 + tid;
-        bool active     = i < p1;
-        int64_t k = 0, v = 0;
-        uint32_t slot = 0;
-        if (active) {
-          k    = d.pk[i];
-          v    = d.pp[i];
-          slot = slot_hash_i64(k) & (kSlots - 1);
-        }
-        while (__any_sync(0xffffffffu, active)) {
-          bool match = false;
-          if (active) {
-            if (!((s.occ[slot >> 5] >> (slot & 31)) & 1u))
-              active = false;
-            else
-              match = (s.skey[slot] == k);
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, match);
-          if (m) {
-            const int leader = __ffs(m) - 1;
-            int base         = 0;
-            if (lane == leader) base = atomicAdd(&s.scnt, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (match) {
-              const int pos = base + __popc(m & lanemask_lt());
-              const int64_t bv = s.spay[slot];
-              if (pos < kOutCap) {
-                s.sout[0][pos] = k;
-                s.sout[1][pos] = bv;
-                s.sout[2][pos] = k;
-                s.sout[3][pos] = v;
-              } else {
-                // staging full (many matches per probe row): direct, uncoalesced emit
-                const int64_t g = (int64_t)atomicAdd(d.out_count, 1ull);
-                if (g < d.out_capacity) {
-                  d.out[0][g] = k;
-                  d.out[1][g] = bv;
-                  d.out[2][g] = k;
-                  d.out[3][g] = v;
-                }
-              }
+    if (is_producer) {
+      // ------------------------------------------------------------ producer (one lane)
+      if (lane == 0) {
+        for (int lb = next_valid_bucket(s, 0, nd); lb < nd; lb = next_valid_bucket(s, lb + 1, nd)) {
+          const int64_t b1 = s.dboff[lb + 1], p0 = s.dpoff[lb], p1 = s.dpoff[lb + 1];
+          for (int64_t c0 = s.dboff[lb]; c0 < b1; c0 += C::kBuildChunk) {
+            {
+              const int bs = u & 1;
+              const int n  = (int)min((int64_t)C::kBuildChunk, b1 - c0);
+              mbar_wait(&s.empty_build[bs], ((u >> 1) & 1) ^ 1);
+              const Window wk = window_of(d.bk + c0, n), wp = window_of(d.bp + c0, n);
+              mbar_expect_tx(&s.full_build[bs], wk.bytes + wp.bytes);
+              tma_load(s.bkey[bs], wk.base, wk.bytes, &s.full_build[bs]);
+              tma_load(s.bpay[bs], wp.base, wp.bytes, &s.full_build[bs]);
+              u++;
+            }
+            for (int64_t r0 = p0; r0 < p1; r0 += C::kProbeChunk) {
+              const int st = q % C::kProbeStages;
+              const int n  = (int)min((int64_t)C::kProbeChunk, p1 - r0);
+              mbar_wait(&s.empty_probe[st], ((q / C::kProbeStages) & 1) ^ 1);
+              const Window wk = window_of(d.pk + r0, n), wp = window_of(d.pp + r0, n);
+              mbar_expect_tx(&s.full_probe[st], wk.bytes + wp.bytes);
+              tma_load(s.pkey[st], wk.base, wk.bytes, &s.full_probe[st]);
+              tma_load(s.ppay[st], wp.base, wp.bytes, &s.full_probe[st]);
+              q++;
             }
           }
-          if (active) slot = (slot + 1) & (kSlots - 1);
         }
-        // barrier + uniform decision in one: the last emitting warp sees the final count
-        const int need = __syncthreads_or(s.scnt > kFlushAt);
-        if (need) flush_staging(s, d, s.scnt);
+      }
+      __syncwarp();  // reconverge before the CTA-wide barrier at the top of the loop
+    } else {
+      // ------------------------------------------------------------ consumers
+      for (int lb = next_valid_bucket(s, 0, nd); lb < nd; lb = next_valid_bucket(s, lb + 1, nd)) {
+        const int64_t b1 = s.dboff[lb + 1], p0 = s.dpoff[lb], p1 = s.dpoff[lb + 1];
+        for (int64_t c0 = s.dboff[lb]; c0 < b1; c0 += C::kBuildChunk) {
+          // ---- build: fingerprint + row index into a 32-bit slot claimed with atomicCAS; the
+          //      staged rows themselves are the row store (no copy)
+          const int bs = u & 1;
+          const int nb = (int)min((int64_t)C::kBuildChunk, b1 - c0);
+          uint32_t* slots     = s.slots[bs];
+          const int64_t* bkey = s.bkey[bs] + skip_of(d.bk + c0);
+          const int64_t* bpay = s.bpay[bs] + skip_of(d.bp + c0);
+          mbar_wait(&s.full_build[bs], (u >> 1) & 1);
+          for (int r = tid; r < nb; r += kConsumers) {
+            const uint32_t h = slot_hash_i64(bkey[r]);
+            const uint32_t e = (slot_tag(h) << 11) | (uint32_t)r;
+            uint32_t slot    = h & (C::kSlots - 1);
+            while (atomicCAS(&slots[slot], 0u, e) != 0u) slot = (slot + 1) & (C::kSlots - 1);
+          }
+          // the other table was last probed two build jobs ago: clear it for the next job
+          {
+            uint4* other = reinterpret_cast<uint4*>(s.slots[bs ^ 1]);
+            for (int i = tid; i < C::kSlots / 4; i += kConsumers) other[i] = make_uint4(0, 0, 0, 0);
+          }
+          consumer_sync<kConsumers>();  // table complete
+
+          // ---- probe: every warp streams its 32 rows of each staged chunk at its own pace
+          for (int64_t r0 = p0; r0 < p1; r0 += C::kProbeChunk) {
+            const int st = q % C::kProbeStages;
+            const int np = (int)min((int64_t)C::kProbeChunk, p1 - r0);
+            mbar_wait(&s.full_probe[st], (q / C::kProbeStages) & 1);
+            bool alive = tid < np;
+            int64_t k = 0, v = 0;
+            if (alive) {
+              k = s.pkey[st][skip_of(d.pk + r0) + tid];
+              v = s.ppay[st][skip_of(d.pp + r0) + tid];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.empty_probe[st]);  // rows are in registers: release
+            q++;
+
+            const uint32_t h    = slot_hash_i64(k);
+            const uint32_t want = slot_tag(h);
+            uint32_t slot       = h & (C::kSlots - 1);
+            while (true) {
+              bool found = false;
+              int idx    = 0;
+              if (alive) {
+                // walk to the next fingerprint+key match or to the end of the cluster
+                while (true) {
+                  const uint32_t e = slots[slot];
+                  if (e == 0u) {
+                    alive = false;
+                    break;
+                  }
+                  if ((e >> 11) == want) {
+                    idx = (int)(e & 0x7ffu);
+                    if (bkey[idx] == k) {
+                      found = true;
+                      break;
+                    }
+                  }
+                  slot = (slot + 1) & (C::kSlots - 1);
+                }
+              }
+              const unsigned m = __ballot_sync(0xffffffffu, found);
+              if (m == 0) break;
+              const int leader = __ffs(m) - 1;
+              int obase        = 0;
+              if (lane == leader) obase = atomicAdd(&s.scnt[cur], __popc(m));
+              obase         = __shfl_sync(0xffffffffu, obase, leader);
+              const int pos = obase + __popc(m & lanemask_lt());
+              const bool spill = found && pos >= C::kOutRows;
+              if (found && !spill) {
+                s.sout[cur][0][pos] = k;
+                s.sout[cur][1][pos] = bpay[idx];
+                s.sout[cur][2][pos] = k;
+                s.sout[cur][3][pos] = v;
+              }
+              // tile full (high selectivity / duplicates): the warp reserves its own run of
+              // the output with one atomicAdd and stores it directly
+              const unsigned ms = __ballot_sync(0xffffffffu, spill);
+              if (ms) {
+                const int sl = __ffs(ms) - 1;
+                unsigned long long g = 0;
+                if (lane == sl) g = atomicAdd(d.out_count, (unsigned long long)__popc(ms));
+                g = __shfl_sync(0xffffffffu, g, sl);
+                if (spill) {
+                  const int64_t gi = (int64_t)g + __popc(ms & lanemask_lt());
+                  if (gi < d.out_capacity) {
+                    d.out[0][gi] = k;
+                    d.out[1][gi] = bpay[idx];
+                    d.out[2][gi] = k;
+                    d.out[3][gi] = v;
+                  }
+                }
+              }
+              if (found) slot = (slot + 1) & (C::kSlots - 1);  // multimap: scan past the hit
+            }
+          }
+
+          // ---- end of build job: table and row store are released, output tiles rotate
+          if (tid == 0 && pend_n) s.sbase[pend_tile] = pend_base_reg;
+          consumer_sync<kConsumers>();
+          if (lane == 0) mbar_arrive(&s.empty_build[bs]);
+          if (pend_n) {
+            // copy out the tile whose atomicAdd was issued one build job ago (latency hidden);
+            // it stays untouched until the job after next, when every thread is past here
+            const int64_t gb = (int64_t)s.sbase[pend_tile];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+              for (int i = tid; i < pend_n; i += kConsumers)
+                if (gb + i < d.out_capacity) d.out[c][gb + i] = s.sout[pend_tile][c][i];
+            if (tid == 0) s.scnt[pend_tile] = 0;
+            pend_n = 0;
+          }
+          int n_out = s.scnt[cur];
+          if (n_out > 0) {
+            if (n_out > C::kOutRows) n_out = C::kOutRows;
+            if (tid == 0) pend_base_reg = atomicAdd(d.out_count, (unsigned long long)n_out);
+            pend_n    = n_out;
+            pend_tile = cur;
+            cur       = cur + 1 == kOutTiles ? 0 : cur + 1;
+          }
+          u++;
+        }
       }
     }
   }
-  __syncthreads();
-  const int n = s.scnt;
-  __syncthreads();
-  if (n > 0) flush_staging(s, d, n);
+
+  // ---- drain the pending tile (the current one is empty: every job hands its tile over)
+  if (!is_producer) {
+    if (tid == 0 && pend_n) s.sbase[pend_tile] = pend_base_reg;
+    consumer_sync<kConsumers>();
+    if (pend_n) {
+      const int64_t gb = (int64_t)s.sbase[pend_tile];
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        for (int i = tid; i < pend_n; i += kConsumers)
+          if (gb + i < d.out_capacity) d.out[c][gb + i] = s.sout[pend_tile][c][i];
+    }
+  }
 }
 
-// Swap (build, probe) output halves when the caller's left table was used as the probe side.
+int join_shape()
+{
+  static int shape = -1;
+  if (shape < 0) {
+    const char* e = getenv("DJ_JOIN_SHAPE");
+    shape         = (e && (e[0] == 'B' || e[0] == 'b')) ? 1 : 0;
+  }
+  return shape;
+}
+
+template <class C>
+int launch_join(const JoinDev& d, int ctas_per_sm, cudaStream_t stream)
+{
+  const size_t smem = sizeof(JoinSmem<C>);
+  auto kern         = bucket_join_kernel<C>;
+  DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = sm_count() * ctas_per_sm;
+  if (grid > d.nbuckets) grid = d.nbuckets;
+  {
+    ProfScope prof(DJ_PROF_JOIN, stream);
+    kern<<<grid, C::kThreads, smem, stream>>>(d);
+  }
+  DJ_LAUNCH_CHECK();
+  return DJ_OK;
+}
+
 }  // namespace
 
 RadixPlan make_radix_plan(int64_t nbuild)
 {
+  const int target = join_shape() == 1 ? CfgB::kTargetRows : CfgA::kTargetRows;
   RadixPlan p{0, 0, 1};
   int bits = 0;
-  while (bits < 20 && (nbuild >> bits) > kTargetRows) bits++;
+  while (bits < 20 && (nbuild >> bits) > target) bits++;
   if (bits <= 10) {
     p.bits1 = bits;
     p.bits2 = 0;
@@ -195,23 +436,7 @@ int run_bucket_join(const JoinBuffers& jb, bool swap_output_sides, cudaStream_t 
   for (int c = 0; c < 4; c++) d.out[c] = jb.out[swap_output_sides ? (c + 2) % 4 : c];
   d.out_capacity = jb.out_capacity;
   d.out_count    = (unsigned long long*)jb.d_out_count;
-  d.work_counter = jb.d_work_counter;
-
-  const size_t smem = sizeof(JoinSmem);
-  DJ_CUDA_TRY(cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-  int per_sm = 1;
-  DJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_join_kernel,
-                                                            kJoinThreads, smem));
-  if (per_sm < 1) per_sm = 1;
-  int grid = sm_count() * per_sm;
-  if (grid > jb.nbuckets) grid = jb.nbuckets;
-  {
-    ProfScope prof(DJ_PROF_JOIN, stream);
-    bucket_join_kernel<<<grid, kJoinThreads, smem, stream>>>(d);
-  }
-  DJ_LAUNCH_CHECK();
-  return DJ_OK;
+  return join_shape() == 1 ? launch_join<CfgB>(d, 2, stream) : launch_join<CfgA>(d, 1, stream);
 }
 
 }  // namespace dj
