@@ -189,6 +189,68 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums)
   return warp_sums[warp] + incl - v;
 }
 
+// ---------------------------------------------------------------- PTX helpers (mbarrier + TMA)
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_LOOP:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra WAIT_DONE;\n"
+    "bra WAIT_LOOP;\n"
+    "WAIT_DONE:\n"
+    "}\n" ::"r"(smem_u32(bar)),
+    "r"(parity)
+    : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         unsigned long long* bar)
+{
+  asm volatile(
+    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+      smem_u32(smem_dst)),
+    "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+    : "memory");
+}
+
+// 16-byte aligned window covering n int64 starting at p
+struct Window {
+  const char* base;
+  uint32_t bytes;
+};
+__device__ __forceinline__ Window window_of(const int64_t* p, int n)
+{
+  const uintptr_t a  = reinterpret_cast<uintptr_t>(p);
+  const uintptr_t lo = a & ~(uintptr_t)15;
+  const uintptr_t hi = (a + (uintptr_t)n * 8 + 15) & ~(uintptr_t)15;
+  return Window{reinterpret_cast<const char*>(lo), (uint32_t)(hi - lo)};
+}
+__device__ __forceinline__ int skip_of(const int64_t* p)
+{
+  return (int)((reinterpret_cast<uintptr_t>(p) & 15) >> 3);
+}
+
+
 __device__ __forceinline__ unsigned lanemask_lt()
 {
   unsigned m;

@@ -15,6 +15,8 @@
 // src/shuffle_on.cpp:59-60) in mode 0, and is the join's private sub-partitioner in mode 1.
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
+
 #include "dj_device.cuh"
 #include "dj_internal.h"
 
@@ -123,19 +125,29 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(PassDev d)
 
 // ---------------------------------------------------------------- scatter
 // Dynamic shared memory layout (T = kScatterTile):
-//   int64 skey[T]; int64 spay[NPAY][T]; int64 s_delta[F]; int s_start[F]; uint16 sbkt[T]
+//   int4 srow[T] (key, payload 0) | int64 spay[NPAY-1][T] | int64 s_delta[F] | int s_start[F] |
+//   uint16 sbkt[T]
+// The sorted tile is kept as 16-byte rows so that the scattered write and the streaming read are
+// single 128-bit shared-memory accesses (half the wavefronts of two 64-bit ones).
+constexpr int kMaxBinsPerThread = (kMaxFanout + kScatterThreads - 1) / kScatterThreads;
+
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int MODE, int NPAY, bool WARP_AGG>
 __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(PassDev d)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int T = kScatterTile;
-  int64_t* skey   = reinterpret_cast<int64_t*>(smem_raw);
-  int64_t* spay   = skey + T;
-  int64_t* s_delta = spay + (size_t)NPAY * T;
+  constexpr int T  = kScatterTile;
+  int4* srow       = reinterpret_cast<int4*>(smem_raw);
+  int64_t* spay    = reinterpret_cast<int64_t*>(srow + T);
+  int64_t* s_delta = spay + (size_t)(NPAY - 1) * T;
   int* s_start     = reinterpret_cast<int*>(s_delta + d.F);
   uint16_t* sbkt   = reinterpret_cast<uint16_t*>(s_start + d.F);
   __shared__ int warp_sums[33];
-  __shared__ int s_parent;
+  __shared__ int s_parent, s_parent_next;
 
   const int tid   = threadIdx.x;
   const int lane  = tid & 31;
@@ -144,14 +156,33 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(PassDev d)
   const int bpt   = (F + kScatterThreads - 1) / kScatterThreads;
 
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int tn = t + gridDim.x;  // this CTA's next tile: pulled into L2 while this one runs
     for (int i = tid; i < F; i += kScatterThreads) s_start[i] = 0;
     if (tid == 0) s_parent = find_parent(d.scat_tiles, d.P, t);
+    if (tid == 32 && tn < total) s_parent_next = find_parent(d.scat_tiles, d.P, tn);
     __syncthreads();
     const int p       = s_parent;
     const int64_t beg = d.parent_off[p] + (int64_t)(t - d.scat_tiles[p]) * T;
     int64_t end       = beg + T;
     if (end > d.parent_off[p + 1]) end = d.parent_off[p + 1];
     const int tile_n = (int)(end - beg);
+
+    if (tn < total) {
+      const int pn       = s_parent_next;
+      const int64_t nbeg = d.parent_off[pn] + (int64_t)(tn - d.scat_tiles[pn]) * T;
+      int64_t nend       = nbeg + T;
+      if (nend > d.parent_off[pn + 1]) nend = d.parent_off[pn + 1];
+      // T rows = T/16 lines of 128 B per column; one line per thread and column
+      constexpr int kLines = T / 16;
+      for (int l = tid; l < kLines; l += kScatterThreads) {
+        const int64_t row = nbeg + (int64_t)l * 16;
+        if (row < nend) {
+          prefetch_l2(d.in_key + row);
+#pragma unroll
+          for (int c = 0; c < NPAY; c++) prefetch_l2(d.in_pay[c] + row);
+        }
+      }
+    }
 
     // phase 1: load keys, bucket, rank inside the tile's bucket
     int64_t key[kRowsPerThread];
@@ -186,21 +217,25 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(PassDev d)
     }
     __syncthreads();
 
-    // phase 2: exclusive scan of the tile histogram; reserve the tile's slice of each bucket
+    // phase 2: exclusive scan of the tile histogram; reserve the tile's slice of each bucket.
+    // The global atomicAdd results are only consumed after phase 3, hiding their round trip.
+    unsigned long long gres[kMaxBinsPerThread];
+    int grun[kMaxBinsPerThread];
     {
       const int b0 = tid * bpt;
       int sum      = 0;
       for (int k = 0; k < bpt; k++)
         if (b0 + k < F) sum += s_start[b0 + k];
       int run = block_exclusive_scan<kScatterThreads>(sum, warp_sums);
-      for (int k = 0; k < bpt; k++) {
-        if (b0 + k < F) {
+#pragma unroll
+      for (int k = 0; k < kMaxBinsPerThread; k++) {
+        grun[k] = -1;
+        if (k < bpt && b0 + k < F) {
           const int c     = s_start[b0 + k];
           s_start[b0 + k] = run;
           if (c) {
-            unsigned long long g =
-              atomicAdd(&d.cursor[(size_t)p * F + b0 + k], (unsigned long long)c);
-            s_delta[b0 + k] = (int64_t)g - run;
+            gres[k] = atomicAdd(&d.cursor[(size_t)p * F + b0 + k], (unsigned long long)c);
+            grun[k] = run;
           }
           run += c;
         }
@@ -208,30 +243,213 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(PassDev d)
     }
     __syncthreads();
 
-    // phase 3: rows into bucket-sorted order in shared memory (payloads straight from HBM)
+    // phase 3: rows into bucket-sorted order in shared memory (payloads straight from L2/HBM)
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; j++) {
       const int r = j * kScatterThreads + tid;
       if (r < tile_n) {
-        const int b   = brank[j] >> 16;
-        const int pos = s_start[b] + (int)(brank[j] & 0xffffu);
-        skey[pos]     = key[j];
-        sbkt[pos]     = (uint16_t)b;
+        const int b       = brank[j] >> 16;
+        const int pos     = s_start[b] + (int)(brank[j] & 0xffffu);
+        const int64_t pay = d.in_pay[0][beg + r];
+        srow[pos]         = make_int4((int)(uint32_t)(uint64_t)key[j], (int)((uint64_t)key[j] >> 32),
+                                      (int)(uint32_t)(uint64_t)pay, (int)((uint64_t)pay >> 32));
+        sbkt[pos]         = (uint16_t)b;
 #pragma unroll
-        for (int c = 0; c < NPAY; c++) spay[(size_t)c * T + pos] = d.in_pay[c][beg + r];
+        for (int c = 1; c < NPAY; c++) spay[(size_t)(c - 1) * T + pos] = d.in_pay[c][beg + r];
       }
     }
+#pragma unroll
+    for (int k = 0; k < kMaxBinsPerThread; k++)
+      if (grun[k] >= 0) s_delta[tid * bpt + k] = (int64_t)gres[k] - grun[k];
     __syncthreads();
 
     // phase 4: stream the sorted tile out; consecutive threads hit consecutive addresses
     for (int i = tid; i < tile_n; i += kScatterThreads) {
       const int64_t dst = s_delta[sbkt[i]] + i;
-      d.out_key[dst]    = skey[i];
+      const int4 row    = srow[i];
+      d.out_key[dst]    = (int64_t)(((uint64_t)(uint32_t)row.y << 32) | (uint32_t)row.x);
+      d.out_pay[0][dst] = (int64_t)(((uint64_t)(uint32_t)row.w << 32) | (uint32_t)row.z);
 #pragma unroll
-      for (int c = 0; c < NPAY; c++) d.out_pay[c][dst] = spay[(size_t)c * T + i];
+      for (int c = 1; c < NPAY; c++) d.out_pay[c][dst] = spay[(size_t)(c - 1) * T + i];
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------- scatter, TMA-staged
+// One persistent 1024-thread CTA per SM for the key + one payload case.  Input tiles are
+// pulled HBM -> shared memory by TMA bulk copies (cp.async.bulk + mbarrier) two tiles ahead,
+// so the ranking / sorting phases never wait on global loads and HBM stays busy while they
+// run; everything else follows scatter_kernel.  Destination rows are tracked as 32-bit
+// offsets (tables < 2^32 rows).
+constexpr int kTmaThreads = 1024;
+constexpr int kTmaRows    = kScatterTile / kTmaThreads;  // rows per thread and tile
+
+struct TileDesc {
+  int64_t beg;
+  int n;
+  int parent;
+};
+
+struct __align__(128) ScatterTmaSmem {
+  int64_t kst[2][kScatterTile + 2];
+  int64_t pst[2][kScatterTile + 2];
+  int4 srow[kScatterTile];
+  uint16_t sbkt[kScatterTile];
+  int s_start[kMaxFanout];
+  uint32_t s_delta[kMaxFanout];
+  unsigned long long full[2];
+  TileDesc desc[2];
+  int warp_sums[33];
+};
+
+template <int MODE, bool WARP_AGG>
+__global__ void __launch_bounds__(kTmaThreads, 1) scatter_tma_kernel(PassDev d)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ScatterTmaSmem& s = *reinterpret_cast<ScatterTmaSmem*>(smem_raw);
+  constexpr int T   = kScatterTile;
+  const int tid     = threadIdx.x;
+  const int lane    = tid & 31;
+  const int F       = d.F;
+  const int total   = d.scat_tiles[d.P];
+
+  // thread 0 walks this CTA's tiles two ahead of the consumers; parents only move forward
+  int prod_parent = 0;
+  auto issue_tile = [&](int k) {  // thread 0 only
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= total) return;
+    while (d.scat_tiles[prod_parent + 1] <= t) prod_parent++;
+    const int64_t beg = d.parent_off[prod_parent] + (int64_t)(t - d.scat_tiles[prod_parent]) * T;
+    int64_t end       = beg + T;
+    if (end > d.parent_off[prod_parent + 1]) end = d.parent_off[prod_parent + 1];
+    const int st = k & 1;
+    s.desc[st]   = TileDesc{beg, (int)(end - beg), prod_parent};
+    const Window wk = window_of(d.in_key + beg, (int)(end - beg));
+    const Window wp = window_of(d.in_pay[0] + beg, (int)(end - beg));
+    mbar_expect_tx(&s.full[st], wk.bytes + wp.bytes);
+    tma_load(s.kst[st], wk.base, wk.bytes, &s.full[st]);
+    tma_load(s.pst[st], wp.base, wp.bytes, &s.full[st]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&s.full[0], 1);
+    mbar_init(&s.full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue_tile(0);
+    issue_tile(1);
+  }
+
+  for (int k = 0; blockIdx.x + k * (int)gridDim.x < total; k++) {
+    const int st = k & 1;
+    if (tid < F) s.s_start[tid] = 0;
+    __syncthreads();  // previous tile fully written out; descriptors of this tile visible
+    mbar_wait(&s.full[st], (k >> 1) & 1);
+    const TileDesc td  = s.desc[st];
+    const int tile_n   = td.n;
+    const int64_t* kst = s.kst[st] + skip_of(d.in_key + td.beg);
+    const int64_t* pst = s.pst[st] + skip_of(d.in_pay[0] + td.beg);
+
+    // phase 1: keys from the staged tile -> bucket, rank inside the tile's bucket
+    int64_t key[kTmaRows];
+    uint32_t brank[kTmaRows];
+#pragma unroll
+    for (int j = 0; j < kTmaRows; j++) {
+      const int r = j * kTmaThreads + tid;
+      key[j]      = r < tile_n ? kst[r] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kTmaRows; j++) {
+      const int r      = j * kTmaThreads + tid;
+      const bool valid = r < tile_n;
+      const int b      = valid ? bucket_of<MODE>(key[j], d) : 0;
+      int rank;
+      if (WARP_AGG) {
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        rank                 = 0;
+        if (valid) {
+          const unsigned peers = __match_any_sync(vmask, b);
+          const int leader     = __ffs(peers) - 1;
+          int base             = 0;
+          if (lane == leader) base = atomicAdd(&s.s_start[b], __popc(peers));
+          base = __shfl_sync(peers, base, leader);
+          rank = base + __popc(peers & lanemask_lt());
+        }
+      } else {
+        rank = valid ? atomicAdd(&s.s_start[b], 1) : 0;
+      }
+      brank[j] = ((uint32_t)b << 16) | (uint32_t)rank;
+    }
+    __syncthreads();
+
+    // phase 2: exclusive scan of the tile histogram (one bin per thread); reserve the tile's
+    // slice of every bucket -- the atomicAdd results are consumed after phase 3
+    const int cnt = tid < F ? s.s_start[tid] : 0;
+    const int run = block_exclusive_scan<kTmaThreads>(cnt, s.warp_sums);
+    unsigned long long gres = 0;
+    if (tid < F) {
+      s.s_start[tid] = run;
+      if (cnt) gres = atomicAdd(&d.cursor[(size_t)td.parent * F + tid], (unsigned long long)cnt);
+    }
+    __syncthreads();
+
+    // phase 3: rows into bucket-sorted order (16-byte rows) in shared memory
+#pragma unroll
+    for (int j = 0; j < kTmaRows; j++) {
+      const int r = j * kTmaThreads + tid;
+      if (r < tile_n) {
+        const int b       = brank[j] >> 16;
+        const int pos     = s.s_start[b] + (int)(brank[j] & 0xffffu);
+        const int64_t pay = pst[r];
+        s.srow[pos] = make_int4((int)(uint32_t)(uint64_t)key[j], (int)((uint64_t)key[j] >> 32),
+                                (int)(uint32_t)(uint64_t)pay, (int)((uint64_t)pay >> 32));
+        s.sbkt[pos] = (uint16_t)b;
+      }
+    }
+    if (tid < F && cnt) s.s_delta[tid] = (uint32_t)gres - (uint32_t)run;
+    __syncthreads();  // sorted tile complete; the input stage is free again
+
+    if (tid == 0) issue_tile(k + 2);
+
+    // phase 4: stream the sorted tile out; consecutive threads hit consecutive addresses
+#pragma unroll
+    for (int j = 0; j < kTmaRows; j++) {
+      const int i = j * kTmaThreads + tid;
+      if (i < tile_n) {
+        int4 row;
+        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(row.x), "=r"(row.y), "=r"(row.z), "=r"(row.w)
+                     : "r"(smem_u32(&s.srow[i])));
+        const uint32_t dst   = s.s_delta[s.sbkt[i]] + (uint32_t)i;
+        d.out_key[dst]    = (int64_t)(((uint64_t)(uint32_t)row.y << 32) | (uint32_t)row.x);
+        d.out_pay[0][dst] = (int64_t)(((uint64_t)(uint32_t)row.w << 32) | (uint32_t)row.z);
+      }
+    }
+  }
+}
+
+template <int MODE, bool AGG>
+int launch_scatter_tma(const PassDev& dev, cudaStream_t stream)
+{
+  const size_t smem = sizeof(ScatterTmaSmem);
+  auto kern         = scatter_tma_kernel<MODE, AGG>;
+  DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof(DJ_PROF_SCATTER, stream);
+    kern<<<sm_count(), kTmaThreads, smem, stream>>>(dev);
+  }
+  DJ_LAUNCH_CHECK();
+  return DJ_OK;
+}
+
+bool use_tma_scatter()
+{
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DJ_SCATTER");
+    v             = (e && (e[0] == 'L' || e[0] == 'l')) ? 0 : 1;  // DJ_SCATTER=legacy disables it
+  }
+  return v == 1;
 }
 
 size_t scatter_smem_bytes(int npay, int F)
@@ -264,8 +482,11 @@ int launch_scatter_agg(const PassDev& dev, int F, cudaStream_t stream)
 }
 
 template <int MODE>
-int launch_scatter_npay(const PassDev& dev, int npay, int F, cudaStream_t stream)
+int launch_scatter_npay(const PassDev& dev, int npay, int F, int64_t nrows, cudaStream_t stream)
 {
+  if (npay == 1 && nrows < ((int64_t)1 << 32) && use_tma_scatter())
+    return F <= 32 ? launch_scatter_tma<MODE, true>(dev, stream)
+                   : launch_scatter_tma<MODE, false>(dev, stream);
   switch (npay) {
     case 1: return launch_scatter_agg<MODE, 1>(dev, F, stream);
     case 2: return launch_scatter_agg<MODE, 2>(dev, F, stream);
@@ -363,8 +584,8 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
     DJ_CUDA_TRY(cudaMemcpyAsync(cursor, buf.d_child_off, nb * 8, cudaMemcpyDeviceToDevice, stream));
   }
 
-  return desc.mode == 0 ? launch_scatter_npay<0>(dev, desc.npay, desc.F, stream)
-                        : launch_scatter_npay<1>(dev, desc.npay, desc.F, stream);
+  return desc.mode == 0 ? launch_scatter_npay<0>(dev, desc.npay, desc.F, buf.nrows, stream)
+                        : launch_scatter_npay<1>(dev, desc.npay, desc.F, buf.nrows, stream);
 }
 
 }  // namespace dj
