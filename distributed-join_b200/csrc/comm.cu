@@ -448,9 +448,19 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
   DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
   *h_out_count = comm->h_pinned[0];
-  if (*h_out_count > out_capacity) {
-    set_error("join output needs %lld rows, capacity %lld", (long long)*h_out_count, (long long)out_capacity);
-    return DJ_ERR_OVERFLOW;
+  // the overflow verdict is collective: every rank returns DJ_ERR_OVERFLOW if any rank's
+  // output did not fit, so that callers can retry together
+  {
+    int64_t over = *h_out_count > out_capacity ? 1 : 0;
+    std::vector<int64_t> overs(world);
+    rc = dj_comm_allgather_i64(comm, &over, 1, overs.data(), st);
+    if (rc) return rc;
+    for (int r = 0; r < world; r++)
+      if (overs[r]) {
+        set_error("join output does not fit on rank %d (this rank: %lld rows, capacity %lld)", r,
+                  (long long)*h_out_count, (long long)out_capacity);
+        return DJ_ERR_OVERFLOW;
+      }
   }
   return DJ_OK;
 }

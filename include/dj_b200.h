@@ -177,8 +177,9 @@ int dj_comm_recv(dj_comm_t* comm, void* d_buf, int64_t nbytes, int source, void*
  * cudf::concatenate).  Collective over `comm` (NULL or size 1: local join only, :186-199).
  * Output columns are left ++ right: (left key, left payload, right key, right payload).
  * *h_out_count receives this rank's cardinality (the call synchronises the stream once at
- * the end to return it).  If it exceeds out_capacity, DJ_ERR_OVERFLOW is returned and the
- * outputs hold the first out_capacity rows.
+ * the end to return it).  If it exceeds out_capacity on ANY rank, every rank returns
+ * DJ_ERR_OVERFLOW (the verdict is all-gathered) and the outputs hold the first out_capacity
+ * rows; *h_out_count is still exact, so callers can retry together with a larger output.
  */
 typedef struct {
   int over_decom_factor; /* >= 1 (src/distributed_join.hpp:72)              */

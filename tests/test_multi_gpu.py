@@ -1,0 +1,71 @@
+"""Multi-GPU parity (run under torchrun on >= 2 GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/test_multi_gpu.py
+
+Each rank generates its slice with the shared counter-based generator, runs the distributed join through
+the C ABI (hash partition -> NCCL all-to-all -> local join) and the ranks compare, bit-exactly, the global
+cardinality and the order-independent multiset checksum with the CPU oracle's single global join
+(G3, test/compare_against_single_gpu.cu:163-205), plus co-location of keys (G4)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "distributed-join_b200")):
+    sys.path.insert(0, p)
+
+
+def main():
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import djb200 as dj
+    import oracle as O
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    comm = dj.Comm.from_torch_distributed()
+    failures = 0
+    cases = [(1_000_000, 1_000_000, 0.3, True, 1), (1_000_000, 1_000_000, 0.3, True, 4),
+             (500_000, 2_000_000, 0.9, False, 2), (40_000, 40_000, 1.0, True, 1), (3_000_000, 3_000_000, 0.3, True, 1)]
+    for nb, np_, sel, unique, odf in cases:
+        g_d = dj.gen_params(nb, np_, sel, 2 * max(nb, np_), unique)
+        g_o = O.gen_params(nb, np_, sel, 2 * max(nb, np_), unique)
+        (lk, lp), (rk, rp) = dj.generate_tables_distributed(g_d, rank, world, dev)
+        res = dj.distributed_inner_join(comm, lk, lp, rk, rp, odf=odf)
+        ck = dj.multiset_checksum4(*res.cols) if res.n_out else (0, 0)
+        # co-location: every output key of this rank hashes to a bucket owned by this rank
+        if res.n_out:
+            ids = dj.partition_ids(res.cols[0].contiguous(), dj.SEED_NVLINK, world * odf)
+            assert bool((ids % world == rank).all()), "key landed on the wrong rank"
+        t = torch.tensor([res.n_out, ck[0] - (1 << 64) if ck[0] >= (1 << 63) else ck[0],
+                          ck[1] - (1 << 64) if ck[1] >= (1 << 63) else ck[1]], dtype=torch.int64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        n_total = sum(int(x[0]) for x in allt)
+        c0 = sum(int(x[1]) & 0xFFFFFFFFFFFFFFFF for x in allt) & 0xFFFFFFFFFFFFFFFF
+        c1 = sum(int(x[2]) & 0xFFFFFFFFFFFFFFFF for x in allt) & 0xFFFFFFFFFFFFFFFF
+        if rank == 0:
+            tabs = [O.generate_tables_distributed(g_o, r, world) for r in range(world)]
+            gl = (np.concatenate([x[0][0] for x in tabs]), np.concatenate([x[0][1] for x in tabs]))
+            gr = (np.concatenate([x[1][0] for x in tabs]), np.concatenate([x[1][1] for x in tabs]))
+            n_ref, ref = O.inner_join(*gl, *gr)
+            ok = n_total == n_ref and (c0, c1) == O.multiset_checksum4(*ref)
+            print(f"case nb={nb} np={np_} sel={sel} unique={unique} odf={odf}: rows {n_total} vs oracle {n_ref} "
+                  f"-> {'OK' if ok else 'MISMATCH'}", flush=True)
+            failures += 0 if ok else 1
+    comm.destroy()
+    f = torch.tensor([failures], device=dev)
+    dist.broadcast(f, 0)
+    dist.destroy_process_group()
+    if int(f.item()):
+        sys.exit(1)
+    if rank == 0:
+        print("multi-gpu parity: all cases passed", flush=True)
+
+
+if __name__ == "__main__":
+    main()
