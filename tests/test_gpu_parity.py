@@ -173,3 +173,27 @@ def test_full_size_properties_100m(dj, oracle):
     torch.cuda.empty_cache()
     cols2, n2 = dj.inner_join(pk, pp, bk, bp, capacity=n // 2)
     assert n2 == hits and dj.multiset_checksum4(cols2[2], cols2[3], cols2[0], cols2[1]) == ck
+
+
+def test_multi_gpu_parity_under_torchrun():
+    """N >= 2 ranks over NCCL (skipped on a single-GPU box): tests/test_multi_gpu.py under torchrun."""
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join("tests", "test_multi_gpu.py")], cwd=root, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "all cases passed" in r.stdout
