@@ -1,0 +1,52 @@
+#include "communicator.hpp"
+
+#include "bootstrap.hpp"
+#include "error.hpp"
+
+void NCCLCommunicator::initialize()
+{
+  mpi_rank = dj_bootstrap::rank();
+  mpi_size = dj_bootstrap::size();
+  CUDA_RT_CALL(cudaGetDevice(&current_device));
+  // rank 0 draws the ncclUniqueId; the launcher-side rendezvous replaces MPI_Bcast
+  // (src/communicator.cpp:803-806)
+  unsigned char id[128] = {0};
+  if (mpi_rank == 0 && mpi_size > 1) NCCL_CALL(dj_comm_unique_id(id));
+  dj_bootstrap::broadcast_from_root(id, sizeof(id), "nccl_id");
+  NCCL_CALL(dj_comm_create(mpi_rank, mpi_size, mpi_size > 1 ? id : nullptr, &comm));
+  CUDA_RT_CALL(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+  dj_bootstrap::set_communicator(this);
+}
+
+void NCCLCommunicator::start() { NCCL_CALL(dj_comm_group_start(comm)); }
+
+// No staging buffers: the reference copies every message into a freshly allocated 256 B-aligned
+// buffer and back (src/communicator.cpp:820-869); NCCL on NVLink does not need that, and
+// bucket starts produced by libdj_b200 are 8 B-aligned rows of 256 B-aligned columns.
+void NCCLCommunicator::send(const void* buf, int64_t count, int element_size, int dest)
+{
+  if (count > 0) NCCL_CALL(dj_comm_send(comm, buf, count * element_size, dest, comm_stream));
+}
+
+void NCCLCommunicator::recv(void* buf, int64_t count, int element_size, int source)
+{
+  if (count > 0) NCCL_CALL(dj_comm_recv(comm, buf, count * element_size, source, comm_stream));
+}
+
+void NCCLCommunicator::stop()
+{
+  NCCL_CALL(dj_comm_group_end(comm));
+  CUDA_RT_CALL(cudaStreamSynchronize(comm_stream));
+}
+
+void NCCLCommunicator::allgather_i64(const int64_t* mine, int n, int64_t* all)
+{
+  NCCL_CALL(dj_comm_allgather_i64(comm, mine, n, all, comm_stream));
+}
+
+void NCCLCommunicator::finalize()
+{
+  CUDA_RT_CALL(cudaStreamDestroy(comm_stream));
+  NCCL_CALL(dj_comm_destroy(comm));
+  comm = nullptr;
+}
