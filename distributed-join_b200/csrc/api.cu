@@ -1,5 +1,6 @@
 // api.cu -- C ABI entry points for the single-GPU stages (include/dj_b200.h):
 // dj_hash_partition_i64 and dj_inner_join_i64, plus library bookkeeping.
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -86,23 +87,109 @@ __global__ void set_two_offsets(int64_t* a, int64_t na, int64_t* b, int64_t nb)
 
 }  // namespace
 
-// scratch rows needed by the join's radix passes + offsets + pass workspace
+// Radix plan shared by both sides of one local join.  A segmented input (a received table:
+// one padded piece per source rank) must go through at least one pass, which also compacts it.
+RadixPlan plan_for(int64_t nbuild, bool any_segmented)
+{
+  RadixPlan plan = make_radix_plan(nbuild);
+  if (plan.bits1 == 0 && any_segmented) {
+    plan.bits1    = 1;
+    plan.nbuckets = 2;
+  }
+  return plan;
+}
+
+// scratch for one side: partition passes' outputs, offsets and pass workspaces
+size_t side_ws_bytes(int64_t span_rows, const RadixPlan& plan, int nseg)
+{
+  const int levels = (plan.bits1 > 0) + (plan.bits2 > 0);
+  const int F1 = 1 << plan.bits1, F2 = 1 << plan.bits2;
+  size_t total = 4096;
+  total += (size_t)levels * 2 * align_up((size_t)span_rows * 8 + 64, 256);
+  total += align_up(((size_t)plan.nbuckets + 1) * 8, 256) + align_up(((size_t)F1 + 1) * 8, 256);
+  size_t pw = pass_workspace_bytes(1, F1, nseg);
+  if (plan.bits2) pw = std::max(pw, pass_workspace_bytes(F1, F2));
+  return total + pw + 1024;
+}
+
 static size_t local_join_ws_bytes(int64_t nb, int64_t np)
 {
-  RadixPlan plan = make_radix_plan(nb);
-  const int levels = (plan.bits1 > 0) + (plan.bits2 > 0);
-  size_t total     = 4096;
-  total += (size_t)levels * (align_up((size_t)nb * 8, 256) * 2 + align_up((size_t)np * 8, 256) * 2);
-  total += 2 * align_up(((size_t)plan.nbuckets + 1) * 8, 256);
+  const RadixPlan plan = plan_for(nb, false);
+  return side_ws_bytes(nb, plan, 0) + side_ws_bytes(np, plan, 0) + 8192;
+}
+
+// Radix-partitions one side of a join into plan.nbuckets buckets (0, 1 or 2 passes).
+int prepare_side(const TableInput& in, const RadixPlan& plan, PreparedSide* out, Arena& arena,
+                 cudaStream_t stream)
+{
   const int F1 = 1 << plan.bits1, F2 = 1 << plan.bits2;
-  total += 2 * align_up(((size_t)F1 + 1) * 8, 256);
-  size_t pw = pass_workspace_bytes(1, F1);
-  if (plan.bits2) {
-    size_t pw2 = pass_workspace_bytes(F1, F2);
-    if (pw2 > pw) pw = pw2;
+  int64_t* off = arena.take<int64_t>((size_t)plan.nbuckets + 1);
+  if (!off) {
+    set_error("inner_join: workspace too small");
+    return DJ_ERR_WORKSPACE;
   }
-  total += 2 * pw;
-  return total + 4096;
+  out->d_off = off;
+  if (plan.bits1 == 0) {
+    set_two_offsets<<<1, 1, 0, stream>>>(off, in.nrows, off, in.nrows);
+    DJ_LAUNCH_CHECK();
+    out->key = in.key;
+    out->pay = in.pay;
+    return DJ_OK;
+  }
+  const size_t pw = std::max(pass_workspace_bytes(1, F1, in.nseg),
+                             plan.bits2 ? pass_workspace_bytes(F1, F2) : (size_t)0);
+  char* pass_ws  = arena.take<char>(pw);
+  int64_t* k1    = arena.take<int64_t>((size_t)in.nrows + 8);
+  int64_t* p1    = arena.take<int64_t>((size_t)in.nrows + 8);
+  int64_t* off1  = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : off;
+  if (!pass_ws || !k1 || !p1 || !off1) {
+    set_error("inner_join: workspace too small");
+    return DJ_ERR_WORKSPACE;
+  }
+  PassDesc d1{1, 0, 0, 32 - plan.bits1, F1, 1, 1};
+  PassBuffers pb{};
+  pb.in_key = in.key; pb.in_pay[0] = in.pay; pb.out_key = k1; pb.out_pay[0] = p1;
+  pb.nrows = in.nrows; pb.d_parent_off = nullptr; pb.d_child_off = off1;
+  if (in.nseg > 0) {
+    pb.d_seg_begin = in.d_seg_begin;
+    pb.d_seg_end   = in.d_seg_end;
+    pb.nseg        = in.nseg;
+  }
+  int rc = run_partition_pass(d1, pb, pass_ws, pw, stream);
+  if (rc) return rc;
+  out->key = k1;
+  out->pay = p1;
+  if (plan.bits2) {
+    int64_t* k2 = arena.take<int64_t>((size_t)in.nrows + 8);
+    int64_t* p2 = arena.take<int64_t>((size_t)in.nrows + 8);
+    if (!k2 || !p2) {
+      set_error("inner_join: workspace too small");
+      return DJ_ERR_WORKSPACE;
+    }
+    PassDesc d2{1, 0, 0, 32 - plan.bits1 - plan.bits2, F2, F1, 1};
+    PassBuffers pb2{};
+    pb2.in_key = k1; pb2.in_pay[0] = p1; pb2.out_key = k2; pb2.out_pay[0] = p2;
+    pb2.nrows = in.nrows; pb2.d_parent_off = off1; pb2.d_child_off = off;
+    rc = run_partition_pass(d2, pb2, pass_ws, pw, stream);
+    if (rc) return rc;
+    out->key = k2;
+    out->pay = p2;
+  }
+  return DJ_OK;
+}
+
+int join_prepared(const PreparedSide& build, const PreparedSide& probe, const RadixPlan& plan,
+                  int64_t* const out[4], int64_t out_capacity, int64_t* d_out_count, bool swap,
+                  cudaStream_t stream)
+{
+  JoinBuffers jb{};
+  jb.bk = build.key; jb.bp = build.pay; jb.d_build_off = build.d_off;
+  jb.pk = probe.key; jb.pp = probe.pay; jb.d_probe_off = probe.d_off;
+  jb.nbuckets = plan.nbuckets;
+  for (int c = 0; c < 4; c++) jb.out[c] = out[c];
+  jb.out_capacity = out_capacity;
+  jb.d_out_count  = d_out_count;
+  return run_bucket_join(jb, swap, stream);
 }
 
 // Joins (bk,bp)[nb] with (pk,pp)[np]; appends matches at *d_out_count (running, device).
@@ -113,86 +200,14 @@ int local_join(const int64_t* bk, const int64_t* bp, int64_t nb, const int64_t* 
                int64_t* d_out_count, bool swap, Arena& arena, cudaStream_t stream)
 {
   if (nb == 0 || np == 0) return DJ_OK;  // src/distributed_join.cpp:76-82
-  const RadixPlan plan = make_radix_plan(nb);
-  const int F1 = 1 << plan.bits1, F2 = 1 << plan.bits2;
-
-  int* work_counter = arena.take<int>(64);
-  int64_t* boff     = arena.take<int64_t>((size_t)plan.nbuckets + 1);
-  int64_t* poff     = arena.take<int64_t>((size_t)plan.nbuckets + 1);
-  if (!work_counter || !boff || !poff) {
-    set_error("inner_join: workspace too small");
-    return DJ_ERR_WORKSPACE;
-  }
-  DJ_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
-
-  const int64_t* jbk = bk;
-  const int64_t* jbp = bp;
-  const int64_t* jpk = pk;
-  const int64_t* jpp = pp;
-
-  if (plan.bits1 == 0) {
-    set_two_offsets<<<1, 1, 0, stream>>>(boff, nb, poff, np);
-    DJ_LAUNCH_CHECK();
-  } else {
-    const size_t pw = plan.bits2 ? (pass_workspace_bytes(F1, F2) > pass_workspace_bytes(1, F1)
-                                      ? pass_workspace_bytes(F1, F2)
-                                      : pass_workspace_bytes(1, F1))
-                                 : pass_workspace_bytes(1, F1);
-    char* pass_ws_b = arena.take<char>(pw);
-    char* pass_ws_p = arena.take<char>(pw);
-    int64_t* b1k    = arena.take<int64_t>((size_t)nb);
-    int64_t* b1p    = arena.take<int64_t>((size_t)nb);
-    int64_t* p1k    = arena.take<int64_t>((size_t)np);
-    int64_t* p1p    = arena.take<int64_t>((size_t)np);
-    int64_t* boff1  = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : boff;
-    int64_t* poff1  = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : poff;
-    if (!pass_ws_b || !pass_ws_p || !b1k || !b1p || !p1k || !p1p || !boff1 || !poff1) {
-      set_error("inner_join: workspace too small");
-      return DJ_ERR_WORKSPACE;
-    }
-    PassDesc d1{1, 0, 0, 32 - plan.bits1, F1, 1, 1};
-    PassBuffers pb{};
-    pb.in_key = bk; pb.in_pay[0] = bp; pb.out_key = b1k; pb.out_pay[0] = b1p;
-    pb.nrows = nb; pb.d_parent_off = nullptr; pb.d_child_off = boff1;
-    int rc = run_partition_pass(d1, pb, pass_ws_b, pw, stream);
-    if (rc) return rc;
-    pb.in_key = pk; pb.in_pay[0] = pp; pb.out_key = p1k; pb.out_pay[0] = p1p;
-    pb.nrows = np; pb.d_child_off = poff1;
-    rc = run_partition_pass(d1, pb, pass_ws_p, pw, stream);
-    if (rc) return rc;
-    jbk = b1k; jbp = b1p; jpk = p1k; jpp = p1p;
-
-    if (plan.bits2) {
-      int64_t* b2k = arena.take<int64_t>((size_t)nb);
-      int64_t* b2p = arena.take<int64_t>((size_t)nb);
-      int64_t* p2k = arena.take<int64_t>((size_t)np);
-      int64_t* p2p = arena.take<int64_t>((size_t)np);
-      if (!b2k || !b2p || !p2k || !p2p) {
-        set_error("inner_join: workspace too small");
-        return DJ_ERR_WORKSPACE;
-      }
-      PassDesc d2{1, 0, 0, 32 - plan.bits1 - plan.bits2, F2, F1, 1};
-      pb.in_key = b1k; pb.in_pay[0] = b1p; pb.out_key = b2k; pb.out_pay[0] = b2p;
-      pb.nrows = nb; pb.d_parent_off = boff1; pb.d_child_off = boff;
-      rc = run_partition_pass(d2, pb, pass_ws_b, pw, stream);
-      if (rc) return rc;
-      pb.in_key = p1k; pb.in_pay[0] = p1p; pb.out_key = p2k; pb.out_pay[0] = p2p;
-      pb.nrows = np; pb.d_parent_off = poff1; pb.d_child_off = poff;
-      rc = run_partition_pass(d2, pb, pass_ws_p, pw, stream);
-      if (rc) return rc;
-      jbk = b2k; jbp = b2p; jpk = p2k; jpp = p2p;
-    }
-  }
-
-  JoinBuffers jb{};
-  jb.bk = jbk; jb.bp = jbp; jb.d_build_off = boff;
-  jb.pk = jpk; jb.pp = jpp; jb.d_probe_off = poff;
-  jb.nbuckets = plan.nbuckets;
-  for (int c = 0; c < 4; c++) jb.out[c] = out[c];
-  jb.out_capacity   = out_capacity;
-  jb.d_out_count    = d_out_count;
-  jb.d_work_counter = work_counter;
-  return run_bucket_join(jb, swap, stream);
+  const RadixPlan plan = plan_for(nb, false);
+  TableInput tb{bk, bp, nb, nullptr, nullptr, 0}, tp{pk, pp, np, nullptr, nullptr, 0};
+  PreparedSide sb{}, sp{};
+  int rc = prepare_side(tb, plan, &sb, arena, stream);
+  if (rc) return rc;
+  rc = prepare_side(tp, plan, &sp, arena, stream);
+  if (rc) return rc;
+  return join_prepared(sb, sp, plan, out, out_capacity, d_out_count, swap, stream);
 }
 
 size_t local_join_workspace(int64_t nb, int64_t np) { return local_join_ws_bytes(nb, np); }

@@ -11,6 +11,7 @@
 //   * batch results are appended into one output (no cudf::concatenate, :333-339).
 #include <nccl.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -31,11 +32,6 @@ struct dj_comm {
 };
 
 namespace dj {
-
-int local_join(const int64_t* bk, const int64_t* bp, int64_t nb, const int64_t* pk,
-               const int64_t* pp, int64_t np, int64_t* const out[4], int64_t out_capacity,
-               int64_t* d_out_count, bool swap, Arena& arena, cudaStream_t stream);
-size_t local_join_workspace(int64_t nb, int64_t np);
 
 #define DJ_NCCL_TRY(expr)                                                                     \
   do {                                                                                        \
@@ -206,21 +202,31 @@ extern "C" int dj_all_to_all(dj_comm_t* c, int group_size, const int* h_group_ra
 // ------------------------------------------------------------------------- distributed join
 
 static const uint32_t kNvlinkSeed = 12345678u;  // src/distributed_join.cpp:211
+// Buckets handed to NCCL start on 32-row (256-byte) boundaries on both the send and the receive
+// side: NCCL's peer copies drop to narrow accesses on pointers that are not 16-byte aligned (the
+// reference works around the same effect with two staging copies, src/communicator.cpp:820-869).
+constexpr int kAlignRows = 32;
+
+static inline int64_t pad_rows(int64_t n) { return (n + kAlignRows - 1) / kAlignRows * kAlignRows; }
 
 static size_t dist_ws_bytes(int64_t nl, int64_t nr, int world, int odf, double slack)
 {
   if (world <= 1) return local_join_workspace(nl < nr ? nl : nr, nl < nr ? nr : nl) + 8192;
   const int nparts = world * odf;
   size_t total     = 1 << 16;
-  // partitioned copies of both tables
-  total += 2 * (align_up((size_t)nl * 8, 256) + align_up((size_t)nr * 8, 256));
-  total += 2 * pass_workspace_bytes(1, nparts) + 2 * align_up(((size_t)nparts + 1) * 8, 256);
-  // receive buffers (balanced estimate with slack)
-  const size_t rl = (size_t)((double)nl * slack) + 4096, rr = (size_t)((double)nr * slack) + 4096;
-  total += 2 * (align_up(rl * 8, 256) + align_up(rr * 8, 256)) + (size_t)odf * 4 * 256;
-  // join scratch for the largest batch
-  const size_t bl = rl / odf + 4096, br = rr / odf + 4096;
-  total += local_join_workspace((int64_t)(bl < br ? bl : br), (int64_t)(bl < br ? br : bl));
+  // partitioned (padded) copies of both tables
+  total += 2 * (align_up((size_t)(nl + (int64_t)nparts * kAlignRows) * 8, 256) +
+                align_up((size_t)(nr + (int64_t)nparts * kAlignRows) * 8, 256));
+  total += 2 * pass_workspace_bytes(1, nparts) + 4 * align_up(((size_t)nparts + 1) * 8, 256);
+  // receive buffers (balanced estimate with slack) + per-source segment tables
+  const size_t rl = (size_t)((double)nl * slack) + (size_t)nparts * kAlignRows + 4096;
+  const size_t rr = (size_t)((double)nr * slack) + (size_t)nparts * kAlignRows + 4096;
+  total += 2 * (align_up(rl * 8, 256) + align_up(rr * 8, 256)) + (size_t)odf * 8 * 256 +
+           (size_t)odf * 4 * align_up((size_t)world * 8, 256);
+  // join scratch for the largest batch (both sides stay alive until the join kernel has run)
+  const int64_t bl = (int64_t)(rl / odf) + 4096, br = (int64_t)(rr / odf) + 4096;
+  const RadixPlan plan = plan_for(bl < br ? bl : br, true);
+  total += side_ws_bytes(bl, plan, world) + side_ws_bytes(br, plan, world);
   return total + 8192;
 }
 
@@ -288,154 +294,183 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   const int G      = world;  // one NVSwitch box: the NVLink group is every rank
   const int nparts = G * odf;
   DJ_REQUIRE(nparts <= kMaxFanout, "distributed_inner_join: %d partitions exceed %d", nparts, kMaxFanout);
-  int rc = ensure_events(comm, odf);
+  int rc = ensure_events(comm, 2 * odf);
   if (rc) return rc;
 
-  // ---- 1. hash partition both tables into G*odf buckets (src/distributed_join.cpp:213-225)
-  const size_t pw  = pass_workspace_bytes(1, nparts);
-  char* pws_l      = arena.take<char>(pw);
-  char* pws_r      = arena.take<char>(pw);
-  int64_t* plk     = arena.take<int64_t>((size_t)nleft);
-  int64_t* plp     = arena.take<int64_t>((size_t)nleft);
-  int64_t* prk     = arena.take<int64_t>((size_t)nright);
-  int64_t* prp     = arena.take<int64_t>((size_t)nright);
-  int64_t* d_off_l = arena.take<int64_t>((size_t)nparts + 1);
-  int64_t* d_off_r = arena.take<int64_t>((size_t)nparts + 1);
-  if (!pws_l || !pws_r || !plk || !plp || !prk || !prp || !d_off_l || !d_off_r) {
-    set_error("distributed_inner_join: workspace too small for the partitioned tables");
-    return DJ_ERR_WORKSPACE;
+  // ---- 1. hash partition both tables into G*odf buckets (src/distributed_join.cpp:213-225);
+  //         bucket starts are padded to kAlignRows so NCCL can send straight from them
+  const int64_t n_in[2]        = {nleft, nright};
+  const int64_t* in_key[2]     = {d_left_key, d_right_key};
+  const int64_t* in_pay[2]     = {d_left_payload, d_right_payload};
+  const size_t pw              = pass_workspace_bytes(1, nparts);
+  int64_t *pk[2], *pp[2], *d_off[2], *d_cnt[2];
+  for (int t = 0; t < 2; t++) {
+    char* pws         = arena.take<char>(pw);
+    const size_t rows = (size_t)(n_in[t] + (int64_t)nparts * kAlignRows);
+    pk[t]             = arena.take<int64_t>(rows);
+    pp[t]             = arena.take<int64_t>(rows);
+    d_off[t]          = arena.take<int64_t>((size_t)nparts + 1);
+    d_cnt[t]          = arena.take<int64_t>((size_t)nparts + 1);
+    if (!pws || !pk[t] || !pp[t] || !d_off[t] || !d_cnt[t]) {
+      set_error("distributed_inner_join: workspace too small for the partitioned tables");
+      return DJ_ERR_WORKSPACE;
+    }
+    PassDesc desc{0, kNvlinkSeed, DJ_HASH_MURMUR3, 0, nparts, 1, 1, kAlignRows};
+    PassBuffers pb{};
+    pb.in_key = in_key[t]; pb.in_pay[0] = in_pay[t]; pb.out_key = pk[t]; pb.out_pay[0] = pp[t];
+    pb.nrows = n_in[t]; pb.d_child_off = d_off[t]; pb.d_child_cnt = d_cnt[t];
+    rc = run_partition_pass(desc, pb, pws, pw, st);
+    if (rc) return rc;
   }
-  PassDesc desc{0, kNvlinkSeed, DJ_HASH_MURMUR3, 0, nparts, 1, 1};
-  PassBuffers pb{};
-  pb.in_key = d_left_key; pb.in_pay[0] = d_left_payload; pb.out_key = plk; pb.out_pay[0] = plp;
-  pb.nrows = nleft; pb.d_child_off = d_off_l;
-  rc = run_partition_pass(desc, pb, pws_l, pw, st);
-  if (rc) return rc;
-  pb.in_key = d_right_key; pb.in_pay[0] = d_right_payload; pb.out_key = prk; pb.out_pay[0] = prp;
-  pb.nrows = nright; pb.d_child_off = d_off_r;
-  rc = run_partition_pass(desc, pb, pws_r, pw, st);
-  if (rc) return rc;
 
-  // ---- 2. sizes: offsets to the host, counts all-gathered over NCCL (communicate_sizes)
-  std::vector<int64_t> off_l(nparts + 1), off_r(nparts + 1);
-  int64_t* hp = comm->h_pinned + 4096;
-  DJ_CUDA_TRY(cudaMemcpyAsync(hp, d_off_l, (size_t)(nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
-  DJ_CUDA_TRY(cudaMemcpyAsync(hp + nparts + 1, d_off_r, (size_t)(nparts + 1) * 8,
-                              cudaMemcpyDeviceToHost, st));
+  // ---- 2. sizes: offsets and counts to the host, counts all-gathered over NCCL (communicate_sizes)
+  std::vector<int64_t> off[2], cntv[2];
+  int64_t* hp = comm->h_pinned + 8192;
+  for (int t = 0; t < 2; t++) {
+    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)t * 2 * (nparts + 1), d_off[t], (size_t)(nparts + 1) * 8,
+                                cudaMemcpyDeviceToHost, st));
+    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)(t * 2 + 1) * (nparts + 1), d_cnt[t], (size_t)nparts * 8,
+                                cudaMemcpyDeviceToHost, st));
+  }
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(off_l.data(), hp, (size_t)(nparts + 1) * 8);
-  memcpy(off_r.data(), hp + nparts + 1, (size_t)(nparts + 1) * 8);
+  for (int t = 0; t < 2; t++) {
+    off[t].assign(hp + (size_t)t * 2 * (nparts + 1), hp + (size_t)t * 2 * (nparts + 1) + nparts + 1);
+    cntv[t].assign(hp + (size_t)(t * 2 + 1) * (nparts + 1), hp + (size_t)(t * 2 + 1) * (nparts + 1) + nparts);
+  }
   if (timing) {
     opts->t_partition_ms = ms_since(t0);
     printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
   }
-
-  // mine[t*nparts + q] = rows of my table t in bucket q; plus my workspace size for a
-  // collective fits-check
-  std::vector<int64_t> mine(2 * nparts + 1), all((size_t)world * (2 * nparts + 1));
+  std::vector<int64_t> mine(2 * nparts), all((size_t)world * 2 * nparts);
   for (int q = 0; q < nparts; q++) {
-    mine[q]          = off_l[q + 1] - off_l[q];
-    mine[nparts + q] = off_r[q + 1] - off_r[q];
+    mine[q]          = cntv[0][q];
+    mine[nparts + q] = cntv[1][q];
   }
-  mine[2 * nparts] = (int64_t)workspace_bytes;
-  rc = dj_comm_allgather_i64(comm, mine.data(), 2 * nparts + 1, all.data(), st);
+  rc = dj_comm_allgather_i64(comm, mine.data(), 2 * nparts, all.data(), st);
   if (rc) return rc;
-  auto cnt = [&](int src, int table, int q) { return all[(size_t)src * (2 * nparts + 1) + table * nparts + q]; };
+  auto cnt = [&](int src, int table, int q) { return all[(size_t)src * 2 * nparts + table * nparts + q]; };
 
-  // ---- 3. receive layout per batch (allocate_communicated_table, src/all_to_all_comm.cpp:701-729)
-  struct Batch {
-    std::vector<int64_t> recv_off[2];
-    int64_t* key[2];
-    int64_t* pay[2];
+  // ---- 3. receive layout per (batch, table): one padded piece per source rank
+  //         (allocate_communicated_table, src/all_to_all_comm.cpp:701-729)
+  struct Piece {
+    std::vector<int64_t> begin, count;  // per source
+    int64_t span = 0, rows = 0;
+    int64_t *key = nullptr, *pay = nullptr;
+    int64_t *d_seg_begin = nullptr, *d_seg_end = nullptr;
   };
-  std::vector<Batch> batches(odf);
-  bool fits_everywhere = true;
-  for (int r = 0; r < world; r++) {
-    // every rank evaluates every rank's need so that a too-small workspace fails collectively
-    size_t need = arena.used;  // same prefix layout on every rank up to table sizes; estimate
-    size_t recv_total[2] = {0, 0};
-    size_t max_b[2]      = {0, 0};
-    for (int b = 0; b < odf; b++)
-      for (int t = 0; t < 2; t++) {
-        size_t rows = 0;
-        for (int s = 0; s < world; s++) rows += (size_t)cnt(s, t, b * G + r);
-        recv_total[t] += rows;
-        if (rows > max_b[t]) max_b[t] = rows;
+  std::vector<Piece> pieces((size_t)odf * 2);
+  size_t need = arena.used;
+  int64_t max_span[2] = {0, 0}, max_rows[2] = {0, 0};
+  for (int b = 0; b < odf; b++)
+    for (int t = 0; t < 2; t++) {
+      Piece& pc = pieces[(size_t)b * 2 + t];
+      pc.begin.resize(G);
+      pc.count.resize(G);
+      for (int s = 0; s < G; s++) {
+        pc.begin[s] = pc.span;
+        pc.count[s] = cnt(s, t, b * G + rank);
+        pc.span += pad_rows(pc.count[s]);
+        pc.rows += pc.count[s];
       }
-    if (r == rank) {
-      need += 2 * (align_up(recv_total[0] * 8, 256) + align_up(recv_total[1] * 8, 256)) +
-              (size_t)odf * 4 * 256;
-      need += local_join_workspace((int64_t)(max_b[0] < max_b[1] ? max_b[0] : max_b[1]),
-                                   (int64_t)(max_b[0] < max_b[1] ? max_b[1] : max_b[0]));
-      if (need > workspace_bytes) fits_everywhere = false;
+      need += 2 * align_up((size_t)pc.span * 8 + 64, 256) + 2 * align_up((size_t)G * 8, 256) + 1024;
+      max_span[t] = std::max(max_span[t], pc.span);
+      max_rows[t] = std::max(max_rows[t], pc.rows);
     }
-  }
-  // agree on the verdict (one more tiny all-gather keeps every rank in step)
   {
-    int64_t ok = fits_everywhere ? 1 : 0;
+    const RadixPlan worst = plan_for(std::min(max_rows[0], max_rows[1]), true);
+    need += side_ws_bytes(max_span[0], worst, G) + side_ws_bytes(max_span[1], worst, G) + 4096;
+    // agree on the verdict so that a too-small workspace fails on every rank together
+    int64_t ok = need <= workspace_bytes ? 1 : 0;
     std::vector<int64_t> oks(world);
     rc = dj_comm_allgather_i64(comm, &ok, 1, oks.data(), st);
     if (rc) return rc;
     for (int r = 0; r < world; r++)
       if (!oks[r]) {
-        set_error("distributed_inner_join: workspace too small on rank %d for its received partitions", r);
+        set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
+                  "(this rank needs %zu of %zu bytes)", r, need, workspace_bytes);
         return DJ_ERR_WORKSPACE;
       }
   }
-  for (int b = 0; b < odf; b++) {
-    for (int t = 0; t < 2; t++) {
-      auto& ro = batches[b].recv_off[t];
-      ro.assign(G + 1, 0);
-      for (int s = 0; s < G; s++) ro[s + 1] = ro[s] + cnt(s, t, b * G + rank);
-      batches[b].key[t] = arena.take<int64_t>((size_t)ro[G]);
-      batches[b].pay[t] = arena.take<int64_t>((size_t)ro[G]);
-      if (!batches[b].key[t] || !batches[b].pay[t]) {
-        set_error("distributed_inner_join: workspace too small for receive buffers");
-        return DJ_ERR_WORKSPACE;
-      }
+  int64_t* hseg = comm->h_pinned + 32768;  // pinned staging for the segment tables
+  DJ_REQUIRE((size_t)odf * 2 * 2 * G <= 16384, "distributed_inner_join: too many segments");
+  for (size_t i = 0; i < pieces.size(); i++) {
+    Piece& pc      = pieces[i];
+    pc.key         = arena.take<int64_t>((size_t)pc.span + 8);
+    pc.pay         = arena.take<int64_t>((size_t)pc.span + 8);
+    pc.d_seg_begin = arena.take<int64_t>((size_t)G);
+    pc.d_seg_end   = arena.take<int64_t>((size_t)G);
+    if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end) {
+      set_error("distributed_inner_join: workspace too small for receive buffers");
+      return DJ_ERR_WORKSPACE;
     }
+    int64_t* hb = hseg + i * 2 * G;
+    for (int s = 0; s < G; s++) {
+      hb[s]     = pc.begin[s];
+      hb[G + s] = pc.begin[s] + pc.count[s];
+    }
+    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_begin, hb, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_end, hb + G, (size_t)G * 8, cudaMemcpyHostToDevice, st));
   }
 
-  // ---- 4. per batch: one grouped exchange on the comm stream, local join on the caller's
-  //         stream; batch b+1's exchange overlaps batch b's join.
-  std::vector<int> group_ranks(G);
-  for (int i = 0; i < G; i++) group_ranks[i] = i;
+  // ---- 4. exchange table by table and batch by batch on the communicator's stream; an event
+  //         per (batch, table) hands the piece to the compute stream, so the radix passes of one
+  //         table overlap the exchange of the next and batch b+1's exchange overlaps batch b's join
   DJ_CUDA_TRY(cudaEventRecord(comm->ev_ready, st));
   DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_ready, 0));
+  auto tcomm = std::chrono::high_resolution_clock::now();
+  for (int b = 0; b < odf; b++)
+    for (int t = 0; t < 2; t++) {
+      Piece& pc = pieces[(size_t)b * 2 + t];
+      // own bucket: device copy (src/all_to_all_comm.cpp:610-653); the rest over NVLink
+      const int64_t self_q = (int64_t)b * G + rank;
+      if (pc.count[rank] > 0) {
+        DJ_CUDA_TRY(cudaMemcpyAsync(pc.key + pc.begin[rank], pk[t] + off[t][self_q], (size_t)pc.count[rank] * 8,
+                                    cudaMemcpyDeviceToDevice, comm->comm_stream));
+        DJ_CUDA_TRY(cudaMemcpyAsync(pc.pay + pc.begin[rank], pp[t] + off[t][self_q], (size_t)pc.count[rank] * 8,
+                                    cudaMemcpyDeviceToDevice, comm->comm_stream));
+      }
+      DJ_NCCL_TRY(ncclGroupStart());
+      for (int i = 0; i < G; i++) {
+        if (i == rank) continue;
+        const int64_t q = (int64_t)b * G + i, ns = cntv[t][q], nr = pc.count[i];
+        if (ns > 0) {
+          DJ_NCCL_TRY(ncclSend(pk[t] + off[t][q], (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+          DJ_NCCL_TRY(ncclSend(pp[t] + off[t][q], (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+          if (opts) opts->bytes_sent += 16 * ns;
+        }
+        if (nr > 0) {
+          DJ_NCCL_TRY(ncclRecv(pc.key + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+          DJ_NCCL_TRY(ncclRecv(pc.pay + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+        }
+      }
+      DJ_NCCL_TRY(ncclGroupEnd());
+      DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[(size_t)b * 2 + t], comm->comm_stream));
+    }
+  if (timing) {
+    DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
+    opts->t_comm_ms = ms_since(tcomm);
+    for (int b = 0; b < odf; b++)
+      printf("Rank %d: All-to-all communication on batch %d takes %.0fms\n", rank, b, opts->t_comm_ms / odf);
+  }
+
   const size_t join_mark = arena.used;
   for (int b = 0; b < odf; b++) {
-    auto tb = std::chrono::high_resolution_clock::now();
-    const int64_t* send_off[2] = {off_l.data() + (size_t)b * G, off_r.data() + (size_t)b * G};
-    const void* send_cols[4]   = {plk, plp, prk, prp};
-    void* recv_cols[4] = {batches[b].key[0], batches[b].pay[0], batches[b].key[1], batches[b].pay[1]};
-    const int es[2]    = {8, 8};
-    // self partition first (explicit copy, src/all_to_all_comm.cpp:610-653), then the wire
-    DJ_NCCL_TRY(ncclGroupStart());
-    for (int t = 0; t < 2; t++) {
-      rc = dj_all_to_all(comm, G, group_ranks.data(), rank, send_cols + 2 * t, recv_cols + 2 * t,
-                         send_off[t], batches[b].recv_off[t].data(), es, 2, 1, comm->comm_stream);
-      if (rc) return rc;
-      if (opts)
-        for (int i = 0; i < G; i++)
-          if (i != rank) opts->bytes_sent += 16 * (send_off[t][i + 1] - send_off[t][i]);
-    }
-    DJ_NCCL_TRY(ncclGroupEnd());
-    DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[b], comm->comm_stream));
-    if (timing) {
-      DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
-      double ms = ms_since(tb);
-      opts->t_comm_ms += ms;
-      printf("Rank %d: All-to-all communication on batch %d takes %.0fms\n", rank, b, ms);
-    }
-    DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_batch[b], 0));
-    auto tj = std::chrono::high_resolution_clock::now();
-    const int64_t nl = batches[b].recv_off[0][G], nr = batches[b].recv_off[1][G];
+    auto tj          = std::chrono::high_resolution_clock::now();
+    Piece& L         = pieces[(size_t)b * 2];
+    Piece& R         = pieces[(size_t)b * 2 + 1];
     arena.used       = join_mark;  // join scratch is reused batch after batch (same stream)
-    const bool swap  = nr < nl;
-    rc = swap ? local_join(batches[b].key[1], batches[b].pay[1], nr, batches[b].key[0],
-                           batches[b].pay[0], nl, out, out_capacity, d_count, true, arena, st)
-              : local_join(batches[b].key[0], batches[b].pay[0], nl, batches[b].key[1],
-                           batches[b].pay[1], nr, out, out_capacity, d_count, false, arena, st);
+    if (L.rows == 0 || R.rows == 0) continue;  // src/distributed_join.cpp:76-82
+    const bool swap  = R.rows < L.rows;  // build on the smaller side
+    const RadixPlan plan = plan_for(swap ? R.rows : L.rows, true);
+    PreparedSide side[2];
+    for (int t = 0; t < 2; t++) {
+      Piece& pc = t ? R : L;
+      DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_batch[(size_t)b * 2 + t], 0));
+      TableInput in{pc.key, pc.pay, pc.span, pc.d_seg_begin, pc.d_seg_end, G};
+      rc = prepare_side(in, plan, &side[t], arena, st);
+      if (rc) return rc;
+    }
+    rc = join_prepared(side[swap ? 1 : 0], side[swap ? 0 : 1], plan, out, out_capacity, d_count, swap, st);
     if (rc) return rc;
     if (timing) {
       DJ_CUDA_TRY(cudaStreamSynchronize(st));

@@ -23,6 +23,7 @@ struct PassDesc {
   int F;     // fan-out per parent bucket (<= kMaxFanout)
   int P;     // number of parent buckets (1 for a top-level pass, <= kMaxFanout)
   int npay;  // payload columns moved with the key (1..kMaxPayload)
+  int align_rows = 1;  // child buckets start on multiples of this many rows (needs P*F <= 1024)
 };
 
 struct PassBuffers {
@@ -33,9 +34,17 @@ struct PassBuffers {
   int64_t nrows;
   const int64_t* d_parent_off;  // [P+1] absolute row offsets of the parents; nullptr when P == 1
   int64_t* d_child_off;         // [P*F+1] out: absolute row offsets of the child buckets
+  // Optional explicit input segments (override d_parent_off): segment i is rows
+  // [d_seg_begin[i], d_seg_end[i]) of the input and feeds output parent d_seg_parent[i]
+  // (nullptr: parent 0).  Used for received tables, which are one padded piece per source rank.
+  const int64_t* d_seg_begin = nullptr;
+  const int64_t* d_seg_end   = nullptr;
+  const int* d_seg_parent    = nullptr;
+  int nseg                   = 0;
+  int64_t* d_child_cnt       = nullptr;  // [P*F] out (aligned passes): rows per child bucket
 };
 
-size_t pass_workspace_bytes(int P, int F);
+size_t pass_workspace_bytes(int P, int F, int nseg = 0);
 int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws, size_t ws_bytes,
                        cudaStream_t stream);
 
@@ -66,6 +75,25 @@ RadixPlan make_radix_plan(int64_t nbuild);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// One side of a local join as it arrives: a contiguous table, or (received tables) `nseg` pieces
+// [d_seg_begin[i], d_seg_end[i]) of arrays spanning `nrows` rows.
+struct TableInput {
+  const int64_t* key;
+  const int64_t* pay;
+  int64_t nrows;
+  const int64_t* d_seg_begin;
+  const int64_t* d_seg_end;
+  int nseg;
+};
+// The same side radix-partitioned for the join: bucket b = rows [d_off[b], d_off[b+1]).
+struct PreparedSide {
+  const int64_t* key;
+  const int64_t* pay;
+  const int64_t* d_off;
+};
+RadixPlan plan_for(int64_t nbuild, bool any_segmented);
+size_t side_ws_bytes(int64_t span_rows, const RadixPlan& plan, int nseg);
+
 // Simple bump allocator over a caller-provided device workspace.
 struct Arena {
   char* base;
@@ -82,5 +110,16 @@ struct Arena {
     return (T*)(base + off);
   }
 };
+
+
+int prepare_side(const TableInput& in, const RadixPlan& plan, PreparedSide* out, Arena& arena,
+                 cudaStream_t stream);
+int join_prepared(const PreparedSide& build, const PreparedSide& probe, const RadixPlan& plan,
+                  int64_t* const out[4], int64_t out_capacity, int64_t* d_out_count, bool swap,
+                  cudaStream_t stream);
+int local_join(const int64_t* bk, const int64_t* bp, int64_t nb, const int64_t* pk,
+               const int64_t* pp, int64_t np, int64_t* const out[4], int64_t out_capacity,
+               int64_t* d_out_count, bool swap, Arena& arena, cudaStream_t stream);
+size_t local_join_workspace(int64_t nb, int64_t np);
 
 }  // namespace dj

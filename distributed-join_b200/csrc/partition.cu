@@ -35,12 +35,14 @@ struct PassDev {
   const int64_t* in_pay[kMaxPayload];
   int64_t* out_key;
   int64_t* out_pay[kMaxPayload];
-  const int64_t* parent_off;  // [P+1]
+  const int64_t* seg_begin;  // [S] first row of every input segment
+  const int64_t* seg_end;    // [S] one past its last row
+  const int* seg_parent;     // [S] output parent bucket the segment's rows belong to
   unsigned long long* counts;  // [P*F+1]
   unsigned long long* cursor;  // [P*F]
-  const int* hist_tiles;       // [P+1] prefix of hist tiles per parent
-  const int* scat_tiles;       // [P+1] prefix of scatter tiles per parent
-  int P, F;
+  const int* hist_tiles;       // [S+1] prefix of hist tiles per segment
+  const int* scat_tiles;       // [S+1] prefix of scatter tiles per segment
+  int S, P, F;
   uint32_t seed;
   int hash_id, shift, pow2;
 };
@@ -68,31 +70,62 @@ __device__ __forceinline__ int find_parent(const int* prefix, int P, int t)
 }
 
 // ---------------------------------------------------------------- plan
-// One CTA: parent offsets (or {0, n}) -> tile prefix tables for the two tile sizes.
-__global__ void plan_kernel(const int64_t* parent_off_in, int64_t nrows, int P,
-                            int64_t* parent_off_out, int* hist_tiles, int* scat_tiles)
+// One CTA: input segments -> tile prefix tables for the two tile sizes.  Segments come either
+// explicitly (begin/end/parent arrays: e.g. the per-source pieces of a received table), from
+// parent offsets (segment i = parent i), or are the single range [0, nrows).
+__global__ void plan_kernel(const int64_t* parent_off_in, const int64_t* seg_begin_in,
+                            const int64_t* seg_end_in, const int* seg_parent_in, int64_t nrows, int S,
+                            int64_t* seg_begin, int64_t* seg_end, int* seg_parent, int* hist_tiles,
+                            int* scat_tiles)
 {
   __shared__ int warp_sums[33];
   const int tid = threadIdx.x;
   int64_t lo = 0, hi = 0;
-  if (tid < P) {
-    lo = parent_off_in ? parent_off_in[tid] : 0;
-    hi = parent_off_in ? parent_off_in[tid + 1] : nrows;
-    if (!parent_off_in) {
-      parent_off_out[0] = 0;
-      parent_off_out[1] = nrows;
+  if (tid < S) {
+    int parent = tid;
+    if (seg_begin_in) {
+      lo     = seg_begin_in[tid];
+      hi     = seg_end_in[tid];
+      parent = seg_parent_in ? seg_parent_in[tid] : 0;
+    } else if (parent_off_in) {
+      lo = parent_off_in[tid];
+      hi = parent_off_in[tid + 1];
+    } else {
+      lo     = 0;
+      hi     = nrows;
+      parent = 0;
     }
+    seg_begin[tid]  = lo;
+    seg_end[tid]    = hi;
+    seg_parent[tid] = parent;
   }
   int64_t n = hi - lo;
   int ht    = (int)((n + kHistTileRows - 1) / kHistTileRows);
   int st    = (int)((n + kScatterTile - 1) / kScatterTile);
   int he = block_exclusive_scan<1024>(ht, warp_sums);
-  if (tid < P) hist_tiles[tid] = he;
-  if (tid == 0) hist_tiles[P] = warp_sums[32];
+  if (tid < S) hist_tiles[tid] = he;
+  if (tid == 0) hist_tiles[S] = warp_sums[32];
   __syncthreads();
   int se = block_exclusive_scan<1024>(st, warp_sums);
-  if (tid < P) scat_tiles[tid] = se;
-  if (tid == 0) scat_tiles[P] = warp_sums[32];
+  if (tid < S) scat_tiles[tid] = se;
+  if (tid == 0) scat_tiles[S] = warp_sums[32];
+}
+
+// Bucket offsets for a pass whose buckets must start on `align` rows (NCCL sends straight
+// from them): off[i] = exclusive scan of roundup(count[i], align); single CTA, nb <= 1024.
+__global__ void aligned_offsets_kernel(const unsigned long long* counts, int nb, int align,
+                                       int64_t* off, int64_t* cnt_out)
+{
+  __shared__ int warp_sums[33];
+  const int tid = threadIdx.x;
+  const long long c = tid < nb ? (long long)counts[tid] : 0;
+  const int padded  = (int)((c + align - 1) / align);  // in units of `align` rows (fits int)
+  const int e       = block_exclusive_scan<1024>(padded, warp_sums);
+  if (tid < nb) {
+    off[tid] = (int64_t)e * align;
+    if (cnt_out) cnt_out[tid] = c;
+  }
+  if (tid == 0) off[nb] = (int64_t)warp_sums[32] * align;
 }
 
 // ---------------------------------------------------------------- histogram
@@ -102,15 +135,16 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(PassDev d)
   extern __shared__ int s_hist[];
   __shared__ int s_parent;
   const int tid   = threadIdx.x;
-  const int total = d.hist_tiles[d.P];
+  const int total = d.hist_tiles[d.S];
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     for (int i = tid; i < d.F; i += kHistThreads) s_hist[i] = 0;
-    if (tid == 0) s_parent = find_parent(d.hist_tiles, d.P, t);
+    if (tid == 0) s_parent = find_parent(d.hist_tiles, d.S, t);
     __syncthreads();
-    const int p       = s_parent;
-    const int64_t beg = d.parent_off[p] + (int64_t)(t - d.hist_tiles[p]) * kHistTileRows;
+    const int sg      = s_parent;
+    const int p       = d.seg_parent[sg];
+    const int64_t beg = d.seg_begin[sg] + (int64_t)(t - d.hist_tiles[sg]) * kHistTileRows;
     int64_t end       = beg + kHistTileRows;
-    if (end > d.parent_off[p + 1]) end = d.parent_off[p + 1];
+    if (end > d.seg_end[sg]) end = d.seg_end[sg];
 #pragma unroll 8
     for (int64_t i = beg + tid; i < end; i += kHistThreads)
       atomicAdd(&s_hist[bucket_of<MODE>(d.in_key[i], d)], 1);
@@ -152,26 +186,27 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(PassDev d)
   const int tid   = threadIdx.x;
   const int lane  = tid & 31;
   const int F     = d.F;
-  const int total = d.scat_tiles[d.P];
+  const int total = d.scat_tiles[d.S];
   const int bpt   = (F + kScatterThreads - 1) / kScatterThreads;
 
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     const int tn = t + gridDim.x;  // this CTA's next tile: pulled into L2 while this one runs
     for (int i = tid; i < F; i += kScatterThreads) s_start[i] = 0;
-    if (tid == 0) s_parent = find_parent(d.scat_tiles, d.P, t);
-    if (tid == 32 && tn < total) s_parent_next = find_parent(d.scat_tiles, d.P, tn);
+    if (tid == 0) s_parent = find_parent(d.scat_tiles, d.S, t);
+    if (tid == 32 && tn < total) s_parent_next = find_parent(d.scat_tiles, d.S, tn);
     __syncthreads();
-    const int p       = s_parent;
-    const int64_t beg = d.parent_off[p] + (int64_t)(t - d.scat_tiles[p]) * T;
+    const int sg      = s_parent;
+    const int p       = d.seg_parent[sg];
+    const int64_t beg = d.seg_begin[sg] + (int64_t)(t - d.scat_tiles[sg]) * T;
     int64_t end       = beg + T;
-    if (end > d.parent_off[p + 1]) end = d.parent_off[p + 1];
+    if (end > d.seg_end[sg]) end = d.seg_end[sg];
     const int tile_n = (int)(end - beg);
 
     if (tn < total) {
       const int pn       = s_parent_next;
-      const int64_t nbeg = d.parent_off[pn] + (int64_t)(tn - d.scat_tiles[pn]) * T;
+      const int64_t nbeg = d.seg_begin[pn] + (int64_t)(tn - d.scat_tiles[pn]) * T;
       int64_t nend       = nbeg + T;
-      if (nend > d.parent_off[pn + 1]) nend = d.parent_off[pn + 1];
+      if (nend > d.seg_end[pn]) nend = d.seg_end[pn];
       // T rows = T/16 lines of 128 B per column; one line per thread and column
       constexpr int kLines = T / 16;
       for (int l = tid; l < kLines; l += kScatterThreads) {
@@ -312,19 +347,19 @@ __global__ void __launch_bounds__(kTmaThreads, 1) scatter_tma_kernel(PassDev d)
   const int tid     = threadIdx.x;
   const int lane    = tid & 31;
   const int F       = d.F;
-  const int total   = d.scat_tiles[d.P];
+  const int total   = d.scat_tiles[d.S];
 
-  // thread 0 walks this CTA's tiles two ahead of the consumers; parents only move forward
+  // thread 0 walks this CTA's tiles two ahead of the consumers; segments only move forward
   int prod_parent = 0;
   auto issue_tile = [&](int k) {  // thread 0 only
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= total) return;
     while (d.scat_tiles[prod_parent + 1] <= t) prod_parent++;
-    const int64_t beg = d.parent_off[prod_parent] + (int64_t)(t - d.scat_tiles[prod_parent]) * T;
+    const int64_t beg = d.seg_begin[prod_parent] + (int64_t)(t - d.scat_tiles[prod_parent]) * T;
     int64_t end       = beg + T;
-    if (end > d.parent_off[prod_parent + 1]) end = d.parent_off[prod_parent + 1];
+    if (end > d.seg_end[prod_parent]) end = d.seg_end[prod_parent];
     const int st = k & 1;
-    s.desc[st]   = TileDesc{beg, (int)(end - beg), prod_parent};
+    s.desc[st]   = TileDesc{beg, (int)(end - beg), d.seg_parent[prod_parent]};
     const Window wk = window_of(d.in_key + beg, (int)(end - beg));
     const Window wp = window_of(d.in_pay[0] + beg, (int)(end - beg));
     mbar_expect_tx(&s.full[st], wk.bytes + wp.bytes);
@@ -507,14 +542,15 @@ static size_t cub_scan_temp_bytes(size_t n)
   return bytes;
 }
 
-size_t pass_workspace_bytes(int P, int F)
+size_t pass_workspace_bytes(int P, int F, int nseg)
 {
   const size_t nb = (size_t)P * F;
+  const size_t S  = (size_t)(nseg > P ? nseg : P);
   size_t total    = 0;
   total += align_up((nb + 1) * 8, 256);
   total += align_up(nb * 8, 256);
-  total += 256;
-  total += 2 * align_up(((size_t)P + 1) * 4, 256);
+  total += 2 * align_up(S * 8, 256) + align_up(S * 4, 256);
+  total += 2 * align_up((S + 1) * 4, 256);
   total += align_up(cub_scan_temp_bytes(nb + 1), 256);
   return total + 1024;
 }
@@ -525,24 +561,30 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   DJ_REQUIRE(desc.F >= 1 && desc.F <= kMaxFanout, "partition: fan-out %d out of range", desc.F);
   DJ_REQUIRE(desc.P >= 1 && desc.P <= kMaxFanout, "partition: parent count %d out of range", desc.P);
   DJ_REQUIRE(desc.mode == 0 || (desc.F & (desc.F - 1)) == 0, "radix fan-out must be a power of 2");
-  DJ_REQUIRE(desc.P == 1 || buf.d_parent_off != nullptr, "partition: parent offsets missing");
+  const bool explicit_segs = buf.d_seg_begin != nullptr;
+  DJ_REQUIRE(explicit_segs || desc.P == 1 || buf.d_parent_off != nullptr, "partition: parent offsets missing");
+  const int S = explicit_segs ? buf.nseg : desc.P;
+  DJ_REQUIRE(S >= 1 && S <= kMaxFanout, "partition: %d input segments (max %d)", S, kMaxFanout);
   const size_t nb = (size_t)desc.P * desc.F;
+  DJ_REQUIRE(desc.align_rows == 1 || nb <= 1024, "partition: aligned buckets need P*F <= 1024");
   Arena arena(d_ws, ws_bytes);
   auto* counts     = arena.take<unsigned long long>(nb + 1);
   auto* cursor     = arena.take<unsigned long long>(nb);
-  auto* parent_off = arena.take<int64_t>(2);
-  auto* hist_tiles = arena.take<int>(desc.P + 1);
-  auto* scat_tiles = arena.take<int>(desc.P + 1);
+  auto* seg_begin  = arena.take<int64_t>(S);
+  auto* seg_end    = arena.take<int64_t>(S);
+  auto* seg_parent = arena.take<int>(S);
+  auto* hist_tiles = arena.take<int>(S + 1);
+  auto* scat_tiles = arena.take<int>(S + 1);
   size_t cub_bytes = cub_scan_temp_bytes(nb + 1);
   auto* cub_temp   = arena.take<char>(cub_bytes);
-  if (!counts || !cursor || !parent_off || !hist_tiles || !scat_tiles || !cub_temp) {
+  if (!counts || !cursor || !seg_begin || !seg_end || !seg_parent || !hist_tiles || !scat_tiles || !cub_temp) {
     set_error("partition pass: workspace too small (%zu bytes given)", ws_bytes);
     return DJ_ERR_WORKSPACE;
   }
 
   DJ_CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 1) * 8, stream));
-  plan_kernel<<<1, 1024, 0, stream>>>(buf.d_parent_off, buf.nrows, desc.P, parent_off, hist_tiles,
-                                      scat_tiles);
+  plan_kernel<<<1, 1024, 0, stream>>>(buf.d_parent_off, buf.d_seg_begin, buf.d_seg_end, buf.d_seg_parent,
+                                      buf.nrows, S, seg_begin, seg_end, seg_parent, hist_tiles, scat_tiles);
   DJ_LAUNCH_CHECK();
 
   PassDev dev{};
@@ -552,11 +594,14 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
     dev.in_pay[c]  = buf.in_pay[c];
     dev.out_pay[c] = buf.out_pay[c];
   }
-  dev.parent_off = buf.d_parent_off ? buf.d_parent_off : parent_off;
+  dev.seg_begin  = seg_begin;
+  dev.seg_end    = seg_end;
+  dev.seg_parent = seg_parent;
   dev.counts     = counts;
   dev.cursor     = cursor;
   dev.hist_tiles = hist_tiles;
   dev.scat_tiles = scat_tiles;
+  dev.S          = S;
   dev.P          = desc.P;
   dev.F          = desc.F;
   dev.seed       = desc.seed;
@@ -577,15 +622,23 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
 
   {
     ProfScope prof(DJ_PROF_OTHER, stream);
-    DJ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, counts,
-                                              (unsigned long long*)buf.d_child_off, (int)(nb + 1),
-                                              stream));
-    count_launch(2);
+    if (desc.align_rows > 1) {
+      aligned_offsets_kernel<<<1, 1024, 0, stream>>>(counts, (int)nb, desc.align_rows, buf.d_child_off,
+                                                     buf.d_child_cnt);
+      count_launch(1);
+    } else {
+      DJ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, counts,
+                                                (unsigned long long*)buf.d_child_off, (int)(nb + 1),
+                                                stream));
+      count_launch(2);
+    }
     DJ_CUDA_TRY(cudaMemcpyAsync(cursor, buf.d_child_off, nb * 8, cudaMemcpyDeviceToDevice, stream));
   }
 
-  return desc.mode == 0 ? launch_scatter_npay<0>(dev, desc.npay, desc.F, buf.nrows, stream)
-                        : launch_scatter_npay<1>(dev, desc.npay, desc.F, buf.nrows, stream);
+  // 32-bit destination offsets in the TMA kernel: input rows + worst-case padding must fit
+  const int64_t span = buf.nrows + (int64_t)nb * desc.align_rows;
+  return desc.mode == 0 ? launch_scatter_npay<0>(dev, desc.npay, desc.F, span, stream)
+                        : launch_scatter_npay<1>(dev, desc.npay, desc.F, span, stream);
 }
 
 }  // namespace dj
