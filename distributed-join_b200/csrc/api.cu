@@ -108,7 +108,7 @@ size_t side_ws_bytes(int64_t span_rows, const RadixPlan& plan, int nseg)
   total += (size_t)levels * 2 * align_up((size_t)span_rows * 8 + 64, 256);
   total += align_up(((size_t)plan.nbuckets + 1) * 8, 256) + align_up(((size_t)F1 + 1) * 8, 256);
   size_t pw = pass_workspace_bytes(1, F1, nseg);
-  if (plan.bits2) pw = std::max(pw, pass_workspace_bytes(F1, F2));
+  if (plan.bits2) pw = std::max(pw, pass_workspace_bytes(F1, F2, nseg));
   return total + pw + 1024;
 }
 
@@ -137,8 +137,32 @@ int prepare_side(const TableInput& in, const RadixPlan& plan, PreparedSide* out,
     return DJ_OK;
   }
   const size_t pw = std::max(pass_workspace_bytes(1, F1, in.nseg),
-                             plan.bits2 ? pass_workspace_bytes(F1, F2) : (size_t)0);
+                             plan.bits2 ? pass_workspace_bytes(F1, F2, in.nseg) : (size_t)0);
   char* pass_ws  = arena.take<char>(pw);
+  if (in.level1_done) {
+    // the exchange delivered level-1 buckets as (source, bucket) segments: run level 2 only
+    if (!plan.bits2 || !in.d_seg_parent) {
+      set_error("inner_join: fused level 1 needs a two-level plan");
+      return DJ_ERR_ARG;
+    }
+    int64_t* k2 = arena.take<int64_t>((size_t)in.nrows + 8);
+    int64_t* p2 = arena.take<int64_t>((size_t)in.nrows + 8);
+    if (!pass_ws || !k2 || !p2) {
+      set_error("inner_join: workspace too small");
+      return DJ_ERR_WORKSPACE;
+    }
+    PassDesc d2{1, 0, 0, 32 - plan.bits1 - plan.bits2, F2, F1, 1};
+    PassBuffers pb2{};
+    pb2.in_key = in.key; pb2.in_pay[0] = in.pay; pb2.out_key = k2; pb2.out_pay[0] = p2;
+    pb2.nrows = in.nrows; pb2.d_parent_off = nullptr; pb2.d_child_off = off;
+    pb2.d_seg_begin = in.d_seg_begin; pb2.d_seg_end = in.d_seg_end; pb2.d_seg_parent = in.d_seg_parent;
+    pb2.nseg = in.nseg;
+    int rc2 = run_partition_pass(d2, pb2, pass_ws, pw, stream);
+    if (rc2) return rc2;
+    out->key = k2;
+    out->pay = p2;
+    return DJ_OK;
+  }
   int64_t* k1    = arena.take<int64_t>((size_t)in.nrows + 8);
   int64_t* p1    = arena.take<int64_t>((size_t)in.nrows + 8);
   int64_t* off1  = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : off;

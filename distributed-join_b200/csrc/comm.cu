@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -42,7 +43,7 @@ namespace dj {
     }                                                                                         \
   } while (0)
 
-constexpr size_t kSmallElems = 1 << 16;
+constexpr size_t kSmallElems = 1 << 20;  // int64 entries of pinned + device scratch per communicator
 
 static int ensure_events(dj_comm* c, int n)
 {
@@ -217,16 +218,16 @@ static size_t dist_ws_bytes(int64_t nl, int64_t nr, int world, int odf, double s
   // partitioned (padded) copies of both tables
   total += 2 * (align_up((size_t)(nl + (int64_t)nparts * kAlignRows) * 8, 256) +
                 align_up((size_t)(nr + (int64_t)nparts * kAlignRows) * 8, 256));
-  total += 2 * pass_workspace_bytes(1, nparts) + 4 * align_up(((size_t)nparts + 1) * 8, 256);
-  // receive buffers (balanced estimate with slack) + per-source segment tables
+  total += 2 * pass_workspace_bytes(1, kMaxFanout) + 4 * align_up(((size_t)kMaxFanout + 1) * 8, 256);
+  // receive buffers (balanced estimate with slack) + per-(source, sub-bucket) segment tables
   const size_t rl = (size_t)((double)nl * slack) + (size_t)nparts * kAlignRows + 4096;
   const size_t rr = (size_t)((double)nr * slack) + (size_t)nparts * kAlignRows + 4096;
   total += 2 * (align_up(rl * 8, 256) + align_up(rr * 8, 256)) + (size_t)odf * 8 * 256 +
-           (size_t)odf * 4 * align_up((size_t)world * 8, 256);
+           (size_t)odf * 2 * 3 * align_up((size_t)kMaxFanout * 8, 256);
   // join scratch for the largest batch (both sides stay alive until the join kernel has run)
   const int64_t bl = (int64_t)(rl / odf) + 4096, br = (int64_t)(rr / odf) + 4096;
   const RadixPlan plan = plan_for(bl < br ? bl : br, true);
-  total += side_ws_bytes(bl, plan, world) + side_ws_bytes(br, plan, world);
+  total += side_ws_bytes(bl, plan, kMaxFanout) + side_ws_bytes(br, plan, kMaxFanout);
   return total + 8192;
 }
 
@@ -294,28 +295,63 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   const int G      = world;  // one NVSwitch box: the NVLink group is every rank
   const int nparts = G * odf;
   DJ_REQUIRE(nparts <= kMaxFanout, "distributed_inner_join: %d partitions exceed %d", nparts, kMaxFanout);
+  DJ_REQUIRE(nleft < ((int64_t)1 << 31) && nright < ((int64_t)1 << 31),
+             "distributed_inner_join: per-rank tables are limited to 2^31 rows");
   int rc = ensure_events(comm, 2 * odf);
   if (rc) return rc;
 
-  // ---- 1. hash partition both tables into G*odf buckets (src/distributed_join.cpp:213-225);
-  //         bucket starts are padded to kAlignRows so NCCL can send straight from them
-  const int64_t n_in[2]        = {nleft, nright};
-  const int64_t* in_key[2]     = {d_left_key, d_right_key};
-  const int64_t* in_pay[2]     = {d_left_payload, d_right_payload};
-  const size_t pw              = pass_workspace_bytes(1, nparts);
+  // ---- 0. agree on the join's radix plan from the global table sizes.  When the plan has two
+  //         levels, the first one is FUSED into the rank partition on the sender: bucket =
+  //         (destination, sub-bucket), so the receiver only runs the second level.
+  int sub_bits = 0;
+  RadixPlan plan{0, 0, 1};
+  {
+    int64_t sizes[2] = {nleft, nright};
+    std::vector<int64_t> alls((size_t)world * 2);
+    rc = dj_comm_allgather_i64(comm, sizes, 2, alls.data(), st);
+    if (rc) return rc;
+    int64_t tot[2] = {0, 0};
+    for (int r = 0; r < world; r++) {
+      tot[0] += alls[(size_t)r * 2];
+      tot[1] += alls[(size_t)r * 2 + 1];
+    }
+    const int64_t est_build = std::min(tot[0], tot[1]) / nparts + 1;  // rows per rank and batch
+    plan                    = plan_for(est_build, true);
+    const int bits          = plan.bits1 + plan.bits2;
+    int fit                 = 0;  // largest sub_bits with nparts << sub_bits <= kMaxFanout
+    while ((nparts << (fit + 1)) <= kMaxFanout) fit++;
+    const char* nofuse = getenv("DJ_NO_FUSE");
+    if (plan.bits2 > 0 && fit > 0 && !(nofuse && nofuse[0] == '1')) {
+      const int b1 = std::min(plan.bits1, fit);
+      if (bits - b1 <= 10) {
+        sub_bits   = b1;
+        plan.bits1 = b1;
+        plan.bits2 = bits - b1;
+      }
+    }
+  }
+  const int F1s = 1 << sub_bits;     // sub-buckets per destination in the sender's partition
+  const int nbk = nparts << sub_bits;  // buckets of the sender's partition
+
+  // ---- 1. hash partition both tables (src/distributed_join.cpp:213-225); every destination's
+  //         run of buckets starts on kAlignRows so NCCL can send straight from it
+  const int64_t n_in[2]    = {nleft, nright};
+  const int64_t* in_key[2] = {d_left_key, d_right_key};
+  const int64_t* in_pay[2] = {d_left_payload, d_right_payload};
+  const size_t pw          = pass_workspace_bytes(1, nbk);
   int64_t *pk[2], *pp[2], *d_off[2], *d_cnt[2];
   for (int t = 0; t < 2; t++) {
     char* pws         = arena.take<char>(pw);
     const size_t rows = (size_t)(n_in[t] + (int64_t)nparts * kAlignRows);
     pk[t]             = arena.take<int64_t>(rows);
     pp[t]             = arena.take<int64_t>(rows);
-    d_off[t]          = arena.take<int64_t>((size_t)nparts + 1);
-    d_cnt[t]          = arena.take<int64_t>((size_t)nparts + 1);
+    d_off[t]          = arena.take<int64_t>((size_t)nbk + 1);
+    d_cnt[t]          = arena.take<int64_t>((size_t)nbk + 1);
     if (!pws || !pk[t] || !pp[t] || !d_off[t] || !d_cnt[t]) {
       set_error("distributed_inner_join: workspace too small for the partitioned tables");
       return DJ_ERR_WORKSPACE;
     }
-    PassDesc desc{0, kNvlinkSeed, DJ_HASH_MURMUR3, 0, nparts, 1, 1, kAlignRows};
+    PassDesc desc{sub_bits ? 2 : 0, kNvlinkSeed, DJ_HASH_MURMUR3, 0, nbk, 1, 1, kAlignRows, nparts, sub_bits};
     PassBuffers pb{};
     pb.in_key = in_key[t]; pb.in_pay[0] = in_pay[t]; pb.out_key = pk[t]; pb.out_pay[0] = pp[t];
     pb.nrows = n_in[t]; pb.d_child_off = d_off[t]; pb.d_child_cnt = d_cnt[t];
@@ -325,60 +361,66 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
 
   // ---- 2. sizes: offsets and counts to the host, counts all-gathered over NCCL (communicate_sizes)
   std::vector<int64_t> off[2], cntv[2];
-  int64_t* hp = comm->h_pinned + 8192;
+  int64_t* hp = comm->h_pinned + (256 << 10);
   for (int t = 0; t < 2; t++) {
-    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)t * 2 * (nparts + 1), d_off[t], (size_t)(nparts + 1) * 8,
+    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)t * 2 * (nbk + 1), d_off[t], (size_t)(nbk + 1) * 8,
                                 cudaMemcpyDeviceToHost, st));
-    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)(t * 2 + 1) * (nparts + 1), d_cnt[t], (size_t)nparts * 8,
+    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)(t * 2 + 1) * (nbk + 1), d_cnt[t], (size_t)nbk * 8,
                                 cudaMemcpyDeviceToHost, st));
   }
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
   for (int t = 0; t < 2; t++) {
-    off[t].assign(hp + (size_t)t * 2 * (nparts + 1), hp + (size_t)t * 2 * (nparts + 1) + nparts + 1);
-    cntv[t].assign(hp + (size_t)(t * 2 + 1) * (nparts + 1), hp + (size_t)(t * 2 + 1) * (nparts + 1) + nparts);
+    off[t].assign(hp + (size_t)t * 2 * (nbk + 1), hp + (size_t)t * 2 * (nbk + 1) + nbk + 1);
+    cntv[t].assign(hp + (size_t)(t * 2 + 1) * (nbk + 1), hp + (size_t)(t * 2 + 1) * (nbk + 1) + nbk);
   }
   if (timing) {
     opts->t_partition_ms = ms_since(t0);
     printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
   }
-  std::vector<int64_t> mine(2 * nparts), all((size_t)world * 2 * nparts);
-  for (int q = 0; q < nparts; q++) {
-    mine[q]          = cntv[0][q];
-    mine[nparts + q] = cntv[1][q];
+  std::vector<int64_t> mine((size_t)2 * nbk), all((size_t)world * 2 * nbk);
+  for (int q = 0; q < nbk; q++) {
+    mine[q]       = cntv[0][q];
+    mine[nbk + q] = cntv[1][q];
   }
-  rc = dj_comm_allgather_i64(comm, mine.data(), 2 * nparts, all.data(), st);
+  rc = dj_comm_allgather_i64(comm, mine.data(), 2 * nbk, all.data(), st);
   if (rc) return rc;
-  auto cnt = [&](int src, int table, int q) { return all[(size_t)src * 2 * nparts + table * nparts + q]; };
+  // rows of source `src`'s table `table` in sub-bucket `sub` of destination bucket q
+  auto cnt = [&](int src, int table, int q, int sub) {
+    return all[(size_t)src * 2 * nbk + (size_t)table * nbk + ((size_t)q << sub_bits) + sub];
+  };
 
-  // ---- 3. receive layout per (batch, table): one padded piece per source rank
-  //         (allocate_communicated_table, src/all_to_all_comm.cpp:701-729)
+  // ---- 3. receive layout per (batch, table): one padded piece per source rank, holding that
+  //         source's F1s sub-buckets back to back (allocate_communicated_table,
+  //         src/all_to_all_comm.cpp:701-729)
   struct Piece {
     std::vector<int64_t> begin, count;  // per source
     int64_t span = 0, rows = 0;
     int64_t *key = nullptr, *pay = nullptr;
     int64_t *d_seg_begin = nullptr, *d_seg_end = nullptr;
+    int* d_seg_parent = nullptr;
   };
+  const int nseg = G * F1s;
   std::vector<Piece> pieces((size_t)odf * 2);
   size_t need = arena.used;
-  int64_t max_span[2] = {0, 0}, max_rows[2] = {0, 0};
+  int64_t max_span[2] = {0, 0};
   for (int b = 0; b < odf; b++)
     for (int t = 0; t < 2; t++) {
       Piece& pc = pieces[(size_t)b * 2 + t];
       pc.begin.resize(G);
       pc.count.resize(G);
       for (int s = 0; s < G; s++) {
+        int64_t c = 0;
+        for (int sub = 0; sub < F1s; sub++) c += cnt(s, t, b * G + rank, sub);
         pc.begin[s] = pc.span;
-        pc.count[s] = cnt(s, t, b * G + rank);
-        pc.span += pad_rows(pc.count[s]);
-        pc.rows += pc.count[s];
+        pc.count[s] = c;
+        pc.span += pad_rows(c);
+        pc.rows += c;
       }
-      need += 2 * align_up((size_t)pc.span * 8 + 64, 256) + 2 * align_up((size_t)G * 8, 256) + 1024;
+      need += 2 * align_up((size_t)pc.span * 8 + 64, 256) + 3 * align_up((size_t)nseg * 8, 256) + 1024;
       max_span[t] = std::max(max_span[t], pc.span);
-      max_rows[t] = std::max(max_rows[t], pc.rows);
     }
   {
-    const RadixPlan worst = plan_for(std::min(max_rows[0], max_rows[1]), true);
-    need += side_ws_bytes(max_span[0], worst, G) + side_ws_bytes(max_span[1], worst, G) + 4096;
+    need += side_ws_bytes(max_span[0], plan, nseg) + side_ws_bytes(max_span[1], plan, nseg) + 4096;
     // agree on the verdict so that a too-small workspace fails on every rank together
     int64_t ok = need <= workspace_bytes ? 1 : 0;
     std::vector<int64_t> oks(world);
@@ -391,51 +433,66 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
         return DJ_ERR_WORKSPACE;
       }
   }
-  int64_t* hseg = comm->h_pinned + 32768;  // pinned staging for the segment tables
-  DJ_REQUIRE((size_t)odf * 2 * 2 * G <= 16384, "distributed_inner_join: too many segments");
+  int64_t* hseg = comm->h_pinned + (512 << 10);  // pinned staging for the segment tables
+  DJ_REQUIRE(pieces.size() * 3 * (size_t)nseg <= (512u << 10), "distributed_inner_join: too many segments");
   for (size_t i = 0; i < pieces.size(); i++) {
-    Piece& pc      = pieces[i];
-    pc.key         = arena.take<int64_t>((size_t)pc.span + 8);
-    pc.pay         = arena.take<int64_t>((size_t)pc.span + 8);
-    pc.d_seg_begin = arena.take<int64_t>((size_t)G);
-    pc.d_seg_end   = arena.take<int64_t>((size_t)G);
-    if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end) {
+    Piece& pc       = pieces[i];
+    const int b     = (int)(i / 2), t = (int)(i % 2);
+    pc.key          = arena.take<int64_t>((size_t)pc.span + 8);
+    pc.pay          = arena.take<int64_t>((size_t)pc.span + 8);
+    pc.d_seg_begin  = arena.take<int64_t>((size_t)nseg);
+    pc.d_seg_end    = arena.take<int64_t>((size_t)nseg);
+    pc.d_seg_parent = arena.take<int>((size_t)nseg);
+    if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) {
       set_error("distributed_inner_join: workspace too small for receive buffers");
       return DJ_ERR_WORKSPACE;
     }
-    int64_t* hb = hseg + i * 2 * G;
+    int64_t* hb = hseg + i * 3 * nseg;
+    int* hpar   = reinterpret_cast<int*>(hb + 2 * (size_t)nseg);
     for (int s = 0; s < G; s++) {
-      hb[s]     = pc.begin[s];
-      hb[G + s] = pc.begin[s] + pc.count[s];
+      int64_t at = pc.begin[s];
+      for (int sub = 0; sub < F1s; sub++) {
+        const int64_t c       = cnt(s, t, b * G + rank, sub);
+        hb[s * F1s + sub]        = at;
+        hb[nseg + s * F1s + sub] = at + c;
+        hpar[s * F1s + sub]      = sub;
+        at += c;
+      }
     }
-    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_begin, hb, (size_t)G * 8, cudaMemcpyHostToDevice, st));
-    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_end, hb + G, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_begin, hb, (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
+    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_end, hb + nseg, (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
+    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_parent, hpar, (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
   }
 
   // ---- 4. exchange table by table and batch by batch on the communicator's stream; an event
-  //         per (batch, table) hands the piece to the compute stream, so the radix passes of one
-  //         table overlap the exchange of the next and batch b+1's exchange overlaps batch b's join
+  //         per (batch, table) hands the piece to the compute stream, so the radix pass of one
+  //         table overlaps the exchange of the next and batch b+1's exchange overlaps batch b's join
   DJ_CUDA_TRY(cudaEventRecord(comm->ev_ready, st));
   DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_ready, 0));
   auto tcomm = std::chrono::high_resolution_clock::now();
   for (int b = 0; b < odf; b++)
     for (int t = 0; t < 2; t++) {
       Piece& pc = pieces[(size_t)b * 2 + t];
+      auto send_begin = [&](int dest) { return off[t][((size_t)b * G + dest) << sub_bits]; };
+      auto send_count = [&](int dest) {
+        int64_t c = 0;
+        for (int sub = 0; sub < F1s; sub++) c += cntv[t][(((size_t)b * G + dest) << sub_bits) + sub];
+        return c;
+      };
       // own bucket: device copy (src/all_to_all_comm.cpp:610-653); the rest over NVLink
-      const int64_t self_q = (int64_t)b * G + rank;
       if (pc.count[rank] > 0) {
-        DJ_CUDA_TRY(cudaMemcpyAsync(pc.key + pc.begin[rank], pk[t] + off[t][self_q], (size_t)pc.count[rank] * 8,
+        DJ_CUDA_TRY(cudaMemcpyAsync(pc.key + pc.begin[rank], pk[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
                                     cudaMemcpyDeviceToDevice, comm->comm_stream));
-        DJ_CUDA_TRY(cudaMemcpyAsync(pc.pay + pc.begin[rank], pp[t] + off[t][self_q], (size_t)pc.count[rank] * 8,
+        DJ_CUDA_TRY(cudaMemcpyAsync(pc.pay + pc.begin[rank], pp[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
                                     cudaMemcpyDeviceToDevice, comm->comm_stream));
       }
       DJ_NCCL_TRY(ncclGroupStart());
       for (int i = 0; i < G; i++) {
         if (i == rank) continue;
-        const int64_t q = (int64_t)b * G + i, ns = cntv[t][q], nr = pc.count[i];
+        const int64_t ns = send_count(i), nr = pc.count[i];
         if (ns > 0) {
-          DJ_NCCL_TRY(ncclSend(pk[t] + off[t][q], (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
-          DJ_NCCL_TRY(ncclSend(pp[t] + off[t][q], (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+          DJ_NCCL_TRY(ncclSend(pk[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+          DJ_NCCL_TRY(ncclSend(pp[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
           if (opts) opts->bytes_sent += 16 * ns;
         }
         if (nr > 0) {
@@ -455,18 +512,17 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
 
   const size_t join_mark = arena.used;
   for (int b = 0; b < odf; b++) {
-    auto tj          = std::chrono::high_resolution_clock::now();
-    Piece& L         = pieces[(size_t)b * 2];
-    Piece& R         = pieces[(size_t)b * 2 + 1];
-    arena.used       = join_mark;  // join scratch is reused batch after batch (same stream)
+    auto tj    = std::chrono::high_resolution_clock::now();
+    Piece& L   = pieces[(size_t)b * 2];
+    Piece& R   = pieces[(size_t)b * 2 + 1];
+    arena.used = join_mark;  // join scratch is reused batch after batch (same stream)
     if (L.rows == 0 || R.rows == 0) continue;  // src/distributed_join.cpp:76-82
-    const bool swap  = R.rows < L.rows;  // build on the smaller side
-    const RadixPlan plan = plan_for(swap ? R.rows : L.rows, true);
+    const bool swap = R.rows < L.rows;         // build on the smaller side
     PreparedSide side[2];
     for (int t = 0; t < 2; t++) {
       Piece& pc = t ? R : L;
       DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_batch[(size_t)b * 2 + t], 0));
-      TableInput in{pc.key, pc.pay, pc.span, pc.d_seg_begin, pc.d_seg_end, G};
+      TableInput in{pc.key, pc.pay, pc.span, pc.d_seg_begin, pc.d_seg_end, nseg, pc.d_seg_parent, sub_bits > 0};
       rc = prepare_side(in, plan, &side[t], arena, st);
       if (rc) return rc;
     }

@@ -15,6 +15,8 @@ constexpr int kMaxFanout  = 1024;
 // Bucket function of one partition pass.
 //   mode 0: (row_hash(key; seed, hash_id)) % F   -- the cuDF-compatible rank partition
 //   mode 1: (local_hash(key) >> shift) & (F-1)   -- the join's private radix sub-partition
+//   mode 2: ((row_hash % nparts) << sub_bits) | (local_hash >> (32 - sub_bits))
+//           -- rank partition fused with the first local radix level (F = nparts << sub_bits)
 struct PassDesc {
   int mode;
   uint32_t seed;
@@ -23,7 +25,10 @@ struct PassDesc {
   int F;     // fan-out per parent bucket (<= kMaxFanout)
   int P;     // number of parent buckets (1 for a top-level pass, <= kMaxFanout)
   int npay;  // payload columns moved with the key (1..kMaxPayload)
-  int align_rows = 1;  // child buckets start on multiples of this many rows (needs P*F <= 1024)
+  int align_rows = 1;  // child buckets start on multiples of this many rows (needs P*F <= 1024);
+                       // in mode 2 only every destination's group of buckets is aligned
+  int nparts   = 0;    // mode 2
+  int sub_bits = 0;    // mode 2
 };
 
 struct PassBuffers {
@@ -84,6 +89,8 @@ struct TableInput {
   const int64_t* d_seg_begin;
   const int64_t* d_seg_end;
   int nseg;
+  const int* d_seg_parent = nullptr;  // level-1 bucket of every segment (only with level1_done)
+  bool level1_done        = false;    // the sender already split the rows into plan.bits1 buckets
 };
 // The same side radix-partitioned for the join: bucket b = rows [d_off[b], d_off[b+1]).
 struct PreparedSide {

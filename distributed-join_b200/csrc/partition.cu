@@ -45,6 +45,7 @@ struct PassDev {
   int S, P, F;
   uint32_t seed;
   int hash_id, shift, pow2;
+  int nparts, sub_bits;  // mode 2: bucket = (row_hash % nparts) << sub_bits | top sub_bits of local_hash
 };
 
 template <int MODE>
@@ -53,8 +54,13 @@ __device__ __forceinline__ int bucket_of(int64_t key, const PassDev& d)
   if (MODE == 0) {
     uint32_t h = row_hash_i64(key, d.seed, d.hash_id);
     return d.pow2 ? (int)(h & (uint32_t)(d.F - 1)) : (int)(h % (uint32_t)d.F);
-  } else {
+  } else if (MODE == 1) {
     return (int)((local_hash_i64(key) >> d.shift) & (uint32_t)(d.F - 1));
+  } else {
+    // fused rank partition + first local radix level: destination-major bucket index
+    const uint32_t h    = row_hash_i64(key, d.seed, d.hash_id);
+    const uint32_t dest = d.pow2 ? (h & (uint32_t)(d.nparts - 1)) : (h % (uint32_t)d.nparts);
+    return (int)((dest << d.sub_bits) | (local_hash_i64(key) >> (32 - d.sub_bits)));
   }
 }
 
@@ -111,21 +117,34 @@ __global__ void plan_kernel(const int64_t* parent_off_in, const int64_t* seg_beg
   if (tid == 0) scat_tiles[S] = warp_sums[32];
 }
 
-// Bucket offsets for a pass whose buckets must start on `align` rows (NCCL sends straight
-// from them): off[i] = exclusive scan of roundup(count[i], align); single CTA, nb <= 1024.
-__global__ void aligned_offsets_kernel(const unsigned long long* counts, int nb, int align,
+// Bucket offsets for a pass whose output is handed to NCCL: buckets are laid out in groups of
+// `group` consecutive buckets (one group per destination rank); every group starts on a multiple
+// of `align` rows, buckets inside a group are contiguous.  Single CTA, nb <= 1024.
+__global__ void aligned_offsets_kernel(const unsigned long long* counts, int nb, int group, int align,
                                        int64_t* off, int64_t* cnt_out)
 {
   __shared__ int warp_sums[33];
+  __shared__ int s_excl[1025];   // exclusive scan of raw counts, in rows
+  __shared__ int s_gstart[1025];  // padded start of every group, in units of `align` rows
   const int tid = threadIdx.x;
-  const long long c = tid < nb ? (long long)counts[tid] : 0;
-  const int padded  = (int)((c + align - 1) / align);  // in units of `align` rows (fits int)
-  const int e       = block_exclusive_scan<1024>(padded, warp_sums);
+  const int c   = tid < nb ? (int)counts[tid] : 0;
+  const int e   = block_exclusive_scan<1024>(c, warp_sums);
+  if (tid < nb) s_excl[tid] = e;
+  if (tid == 0) s_excl[nb] = warp_sums[32];
+  __syncthreads();
+  const int ngroups = nb / group;
+  int padded        = 0;
+  if (tid < ngroups) padded = (s_excl[(tid + 1) * group] - s_excl[tid * group] + align - 1) / align;
+  const int ge = block_exclusive_scan<1024>(padded, warp_sums);
+  if (tid < ngroups) s_gstart[tid] = ge;
+  if (tid == 0) s_gstart[ngroups] = warp_sums[32];
+  __syncthreads();
   if (tid < nb) {
-    off[tid] = (int64_t)e * align;
+    const int g = tid / group;
+    off[tid]    = (int64_t)s_gstart[g] * align + (s_excl[tid] - s_excl[g * group]);
     if (cnt_out) cnt_out[tid] = c;
   }
-  if (tid == 0) off[nb] = (int64_t)warp_sums[32] * align;
+  if (tid == 0) off[nb] = (int64_t)s_gstart[ngroups] * align;
 }
 
 // ---------------------------------------------------------------- histogram
@@ -560,7 +579,9 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
 {
   DJ_REQUIRE(desc.F >= 1 && desc.F <= kMaxFanout, "partition: fan-out %d out of range", desc.F);
   DJ_REQUIRE(desc.P >= 1 && desc.P <= kMaxFanout, "partition: parent count %d out of range", desc.P);
-  DJ_REQUIRE(desc.mode == 0 || (desc.F & (desc.F - 1)) == 0, "radix fan-out must be a power of 2");
+  DJ_REQUIRE(desc.mode != 1 || (desc.F & (desc.F - 1)) == 0, "radix fan-out must be a power of 2");
+  DJ_REQUIRE(desc.mode != 2 || (desc.P == 1 && desc.F == desc.nparts << desc.sub_bits),
+             "fused partition: F must be nparts << sub_bits");
   const bool explicit_segs = buf.d_seg_begin != nullptr;
   DJ_REQUIRE(explicit_segs || desc.P == 1 || buf.d_parent_off != nullptr, "partition: parent offsets missing");
   const int S = explicit_segs ? buf.nseg : desc.P;
@@ -607,7 +628,9 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   dev.seed       = desc.seed;
   dev.hash_id    = desc.hash_id;
   dev.shift      = desc.shift;
-  dev.pow2       = (desc.F & (desc.F - 1)) == 0;
+  dev.pow2       = desc.mode == 2 ? (desc.nparts & (desc.nparts - 1)) == 0 : (desc.F & (desc.F - 1)) == 0;
+  dev.nparts     = desc.nparts;
+  dev.sub_bits   = desc.sub_bits;
 
   const int hist_grid = sm_count() * 4;
   const size_t hsmem  = (size_t)desc.F * sizeof(int);
@@ -615,16 +638,18 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
     ProfScope prof(DJ_PROF_HIST, stream);
     if (desc.mode == 0)
       hist_kernel<0><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
-    else
+    else if (desc.mode == 1)
       hist_kernel<1><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
+    else
+      hist_kernel<2><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
   }
   DJ_LAUNCH_CHECK();
 
   {
     ProfScope prof(DJ_PROF_OTHER, stream);
     if (desc.align_rows > 1) {
-      aligned_offsets_kernel<<<1, 1024, 0, stream>>>(counts, (int)nb, desc.align_rows, buf.d_child_off,
-                                                     buf.d_child_cnt);
+      aligned_offsets_kernel<<<1, 1024, 0, stream>>>(counts, (int)nb, desc.mode == 2 ? 1 << desc.sub_bits : 1,
+                                                     desc.align_rows, buf.d_child_off, buf.d_child_cnt);
       count_launch(1);
     } else {
       DJ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, counts,
@@ -637,8 +662,9 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
 
   // 32-bit destination offsets in the TMA kernel: input rows + worst-case padding must fit
   const int64_t span = buf.nrows + (int64_t)nb * desc.align_rows;
-  return desc.mode == 0 ? launch_scatter_npay<0>(dev, desc.npay, desc.F, span, stream)
-                        : launch_scatter_npay<1>(dev, desc.npay, desc.F, span, stream);
+  if (desc.mode == 0) return launch_scatter_npay<0>(dev, desc.npay, desc.F, span, stream);
+  if (desc.mode == 1) return launch_scatter_npay<1>(dev, desc.npay, desc.F, span, stream);
+  return launch_scatter_npay<2>(dev, desc.npay, desc.F, span, stream);
 }
 
 }  // namespace dj
