@@ -61,7 +61,19 @@ ProfScope::~ProfScope()
   cudaEventRecord(g_prof_recs[slot].b, stream);
 }
 
+// SMs deliberately left idle by the persistent partition kernels while an NCCL exchange is in
+// flight, so that NCCL's copy kernels can become resident next to them (see comm.cu).
+static thread_local int g_sm_reserve = 0;
+void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
+
 int sm_count()
+{
+  const int total = sm_count_physical();
+  const int keep  = total - g_sm_reserve;
+  return keep < total / 2 ? total / 2 : keep;
+}
+
+int sm_count_physical()
 {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;

@@ -24,8 +24,13 @@
 struct dj_comm {
   ncclComm_t nccl = nullptr;
   int rank = 0, size = 1, device = 0;
+  ncclComm_t nccl_ctrl     = nullptr;  // duplicate communicator for counts / verdicts, so that tiny
+                                       // control collectives never queue behind the bulk exchange
   cudaStream_t comm_stream = nullptr;
+  cudaStream_t ctrl_stream = nullptr;
   cudaEvent_t ev_ready     = nullptr;
+  cudaEvent_t ev_part[2]   = {nullptr, nullptr};
+  cudaEvent_t ev_seg[2]    = {nullptr, nullptr};
   std::vector<cudaEvent_t> ev_batch;
   int64_t* h_pinned = nullptr;  // pinned scratch
   int64_t* d_small  = nullptr;  // device scratch for tiny collectives
@@ -80,9 +85,15 @@ extern "C" int dj_comm_create(int rank, int size, const void* h_id128, dj_comm_t
     ncclUniqueId id;
     memcpy(&id, h_id128, sizeof(id));
     DJ_NCCL_TRY(ncclCommInitRank(&c->nccl, size, id, rank));
+    DJ_NCCL_TRY(ncclCommSplit(c->nccl, 0, rank, &c->nccl_ctrl, nullptr));
   }
   DJ_CUDA_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  DJ_CUDA_TRY(cudaStreamCreateWithFlags(&c->ctrl_stream, cudaStreamNonBlocking));
   DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_part[i], cudaEventDisableTiming));
+    DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_seg[i], cudaEventDisableTiming));
+  }
   DJ_CUDA_TRY(cudaMallocHost(&c->h_pinned, kSmallElems * sizeof(int64_t)));
   DJ_CUDA_TRY(cudaMalloc(&c->d_small, kSmallElems * sizeof(int64_t)));
   c->small_elems = kSmallElems;
@@ -94,7 +105,13 @@ extern "C" int dj_comm_destroy(dj_comm_t* c)
 {
   if (!c) return DJ_OK;
   cudaDeviceSynchronize();
+  if (c->nccl_ctrl) ncclCommDestroy(c->nccl_ctrl);
   if (c->nccl) ncclCommDestroy(c->nccl);
+  for (int i = 0; i < 2; i++) {
+    if (c->ev_part[i]) cudaEventDestroy(c->ev_part[i]);
+    if (c->ev_seg[i]) cudaEventDestroy(c->ev_seg[i]);
+  }
+  if (c->ctrl_stream) cudaStreamDestroy(c->ctrl_stream);
   for (auto e : c->ev_batch) cudaEventDestroy(e);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -126,6 +143,27 @@ extern "C" int dj_comm_allgather_i64(dj_comm_t* c, const int64_t* h_mine, int n,
                               cudaMemcpyDeviceToHost, st));
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(h_all, c->h_pinned + n, (size_t)n * c->size * 8);
+  return DJ_OK;
+}
+
+// Control-plane all-gather on the duplicate communicator and its own stream (blocking, tiny).
+static int ctrl_allgather(dj_comm* c, const int64_t* h_mine, int n, int64_t* h_all)
+{
+  if (c->size == 1) {
+    memcpy(h_all, h_mine, (size_t)n * 8);
+    return DJ_OK;
+  }
+  const size_t half = c->small_elems / 2;  // second half of both scratch areas
+  DJ_REQUIRE((size_t)n * (c->size + 1) <= half / 4, "allgather: %d values per rank is too many", n);
+  cudaStream_t st = c->ctrl_stream;
+  int64_t* hs = c->h_pinned + half + half / 2;
+  int64_t* ds = c->d_small + half;
+  memcpy(hs, h_mine, (size_t)n * 8);
+  DJ_CUDA_TRY(cudaMemcpyAsync(ds, hs, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  DJ_NCCL_TRY(ncclAllGather(ds, ds + n, (size_t)n, ncclInt64, c->nccl_ctrl, st));
+  DJ_CUDA_TRY(cudaMemcpyAsync(hs + n, ds + n, (size_t)n * c->size * 8, cudaMemcpyDeviceToHost, st));
+  DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(h_all, hs + n, (size_t)n * c->size * 8);
   return DJ_OK;
 }
 
@@ -308,7 +346,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   {
     int64_t sizes[2] = {nleft, nright};
     std::vector<int64_t> alls((size_t)world * 2);
-    rc = dj_comm_allgather_i64(comm, sizes, 2, alls.data(), st);
+    rc = ctrl_allgather(comm, sizes, 2, alls.data());
     if (rc) return rc;
     int64_t tot[2] = {0, 0};
     for (int r = 0; r < world; r++) {
@@ -330,11 +368,12 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       }
     }
   }
-  const int F1s = 1 << sub_bits;     // sub-buckets per destination in the sender's partition
+  const int F1s = 1 << sub_bits;       // sub-buckets per destination in the sender's partition
   const int nbk = nparts << sub_bits;  // buckets of the sender's partition
+  const int nseg = G * F1s;            // (source, sub-bucket) segments of a received piece
 
-  // ---- 1. hash partition both tables (src/distributed_join.cpp:213-225); every destination's
-  //         run of buckets starts on kAlignRows so NCCL can send straight from it
+  // ---- 1. hash partition both tables (src/distributed_join.cpp:213-225) on the caller's stream;
+  //         every destination's run of buckets starts on kAlignRows so NCCL sends straight from it
   const int64_t n_in[2]    = {nleft, nright};
   const int64_t* in_key[2] = {d_left_key, d_right_key};
   const int64_t* in_pay[2] = {d_left_payload, d_right_payload};
@@ -355,43 +394,22 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     PassBuffers pb{};
     pb.in_key = in_key[t]; pb.in_pay[0] = in_pay[t]; pb.out_key = pk[t]; pb.out_pay[0] = pp[t];
     pb.nrows = n_in[t]; pb.d_child_off = d_off[t]; pb.d_child_cnt = d_cnt[t];
+    // the right table is partitioned while the left one is already on the wire: leave a few
+    // SMs to NCCL's copy kernels (DJ_SM_RESERVE, default 0 = let the hardware interleave)
+    if (t == 1) {
+      const char* e = getenv("DJ_SM_RESERVE");
+      set_sm_reserve(e ? atoi(e) : 0);
+    }
     rc = run_partition_pass(desc, pb, pws, pw, st);
+    set_sm_reserve(0);
     if (rc) return rc;
+    DJ_CUDA_TRY(cudaEventRecord(comm->ev_part[t], st));
   }
 
-  // ---- 2. sizes: offsets and counts to the host, counts all-gathered over NCCL (communicate_sizes)
-  std::vector<int64_t> off[2], cntv[2];
-  int64_t* hp = comm->h_pinned + (256 << 10);
-  for (int t = 0; t < 2; t++) {
-    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)t * 2 * (nbk + 1), d_off[t], (size_t)(nbk + 1) * 8,
-                                cudaMemcpyDeviceToHost, st));
-    DJ_CUDA_TRY(cudaMemcpyAsync(hp + (size_t)(t * 2 + 1) * (nbk + 1), d_cnt[t], (size_t)nbk * 8,
-                                cudaMemcpyDeviceToHost, st));
-  }
-  DJ_CUDA_TRY(cudaStreamSynchronize(st));
-  for (int t = 0; t < 2; t++) {
-    off[t].assign(hp + (size_t)t * 2 * (nbk + 1), hp + (size_t)t * 2 * (nbk + 1) + nbk + 1);
-    cntv[t].assign(hp + (size_t)(t * 2 + 1) * (nbk + 1), hp + (size_t)(t * 2 + 1) * (nbk + 1) + nbk);
-  }
-  if (timing) {
-    opts->t_partition_ms = ms_since(t0);
-    printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
-  }
-  std::vector<int64_t> mine((size_t)2 * nbk), all((size_t)world * 2 * nbk);
-  for (int q = 0; q < nbk; q++) {
-    mine[q]       = cntv[0][q];
-    mine[nbk + q] = cntv[1][q];
-  }
-  rc = dj_comm_allgather_i64(comm, mine.data(), 2 * nbk, all.data(), st);
-  if (rc) return rc;
-  // rows of source `src`'s table `table` in sub-bucket `sub` of destination bucket q
-  auto cnt = [&](int src, int table, int q, int sub) {
-    return all[(size_t)src * 2 * nbk + (size_t)table * nbk + ((size_t)q << sub_bits) + sub];
-  };
-
-  // ---- 3. receive layout per (batch, table): one padded piece per source rank, holding that
-  //         source's F1s sub-buckets back to back (allocate_communicated_table,
-  //         src/all_to_all_comm.cpp:701-729)
+  // ---- 2-4. table by table: sizes (communicate_sizes, on the control communicator), receive
+  //           layout (allocate_communicated_table), exchange.  The left table's exchange starts
+  //           while the right table is still being partitioned; an event per (batch, table) hands
+  //           each received piece to the compute stream, so radix passes overlap later exchanges.
   struct Piece {
     std::vector<int64_t> begin, count;  // per source
     int64_t span = 0, rows = 0;
@@ -399,12 +417,90 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     int64_t *d_seg_begin = nullptr, *d_seg_end = nullptr;
     int* d_seg_parent = nullptr;
   };
-  const int nseg = G * F1s;
   std::vector<Piece> pieces((size_t)odf * 2);
-  size_t need = arena.used;
+  std::vector<int64_t> off[2], cntv[2], allc[2];
+  int64_t* hp   = comm->h_pinned + (256 << 10);  // D2H landing zone for offsets / counts
+  int64_t* hseg = comm->h_pinned + (320 << 10);  // pinned staging for the segment tables
+  DJ_REQUIRE(pieces.size() * 3 * (size_t)nseg <= (192u << 10), "distributed_inner_join: too many segments");
   int64_t max_span[2] = {0, 0};
-  for (int b = 0; b < odf; b++)
-    for (int t = 0; t < 2; t++) {
+  bool exchange_in_flight = false;
+  auto tcomm = std::chrono::high_resolution_clock::now();
+
+  // rows of source `src`'s table t in sub-bucket `sub` of destination bucket q
+  auto cnt = [&](int src, int t, int q, int sub) {
+    return allc[t][(size_t)src * nbk + ((size_t)q << sub_bits) + sub];
+  };
+  auto issue_exchange = [&](int b, int t) -> int {
+    Piece& pc = pieces[(size_t)b * 2 + t];
+    auto send_begin = [&](int dest) { return off[t][((size_t)b * G + dest) << sub_bits]; };
+    auto send_count = [&](int dest) {
+      int64_t c = 0;
+      for (int sub = 0; sub < F1s; sub++) c += cntv[t][(((size_t)b * G + dest) << sub_bits) + sub];
+      return c;
+    };
+    // own bucket: device copy (src/all_to_all_comm.cpp:610-653); the rest over NVLink
+    if (pc.count[rank] > 0) {
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.key + pc.begin[rank], pk[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
+                                  cudaMemcpyDeviceToDevice, comm->comm_stream));
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.pay + pc.begin[rank], pp[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
+                                  cudaMemcpyDeviceToDevice, comm->comm_stream));
+    }
+    DJ_NCCL_TRY(ncclGroupStart());
+    for (int i = 0; i < G; i++) {
+      if (i == rank) continue;
+      const int64_t ns = send_count(i), nr = pc.count[i];
+      if (ns > 0) {
+        DJ_NCCL_TRY(ncclSend(pk[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+        DJ_NCCL_TRY(ncclSend(pp[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+        if (opts) opts->bytes_sent += 16 * ns;
+      }
+      if (nr > 0) {
+        DJ_NCCL_TRY(ncclRecv(pc.key + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+        DJ_NCCL_TRY(ncclRecv(pc.pay + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+      }
+    }
+    DJ_NCCL_TRY(ncclGroupEnd());
+    DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[(size_t)b * 2 + t], comm->comm_stream));
+    exchange_in_flight = true;
+    return DJ_OK;
+  };
+  // collective verdict on the control communicator; drains the bulk stream before failing
+  auto agree_fits = [&](size_t need) -> int {
+    int64_t ok = need <= workspace_bytes ? 1 : 0;
+    std::vector<int64_t> oks(world);
+    int r2 = ctrl_allgather(comm, &ok, 1, oks.data());
+    if (r2) return r2;
+    for (int r = 0; r < world; r++)
+      if (!oks[r]) {
+        if (exchange_in_flight) cudaStreamSynchronize(comm->comm_stream);
+        set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
+                  "(this rank needs %zu of %zu bytes)", r, need, workspace_bytes);
+        return DJ_ERR_WORKSPACE;
+      }
+    return DJ_OK;
+  };
+
+  for (int t = 0; t < 2; t++) {
+    // sizes of table t: wait only for ITS partition pass
+    DJ_CUDA_TRY(cudaStreamWaitEvent(comm->ctrl_stream, comm->ev_part[t], 0));
+    DJ_CUDA_TRY(cudaMemcpyAsync(hp, d_off[t], (size_t)(nbk + 1) * 8, cudaMemcpyDeviceToHost, comm->ctrl_stream));
+    DJ_CUDA_TRY(cudaMemcpyAsync(hp + nbk + 1, d_cnt[t], (size_t)nbk * 8, cudaMemcpyDeviceToHost, comm->ctrl_stream));
+    DJ_CUDA_TRY(cudaStreamSynchronize(comm->ctrl_stream));
+    off[t].assign(hp, hp + nbk + 1);
+    cntv[t].assign(hp + nbk + 1, hp + nbk + 1 + nbk);
+    if (timing && t == 1) {
+      opts->t_partition_ms = ms_since(t0);
+      printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
+      tcomm = std::chrono::high_resolution_clock::now();
+    }
+    allc[t].resize((size_t)world * nbk);
+    rc = ctrl_allgather(comm, cntv[t].data(), nbk, allc[t].data());
+    if (rc) return rc;
+
+    // receive layout: per (batch) one padded piece per source, holding that source's F1s
+    // sub-buckets back to back
+    size_t need = arena.used;
+    for (int b = 0; b < odf; b++) {
       Piece& pc = pieces[(size_t)b * 2 + t];
       pc.begin.resize(G);
       pc.count.resize(G);
@@ -419,96 +515,64 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       need += 2 * align_up((size_t)pc.span * 8 + 64, 256) + 3 * align_up((size_t)nseg * 8, 256) + 1024;
       max_span[t] = std::max(max_span[t], pc.span);
     }
-  {
-    need += side_ws_bytes(max_span[0], plan, nseg) + side_ws_bytes(max_span[1], plan, nseg) + 4096;
-    // agree on the verdict so that a too-small workspace fails on every rank together
-    int64_t ok = need <= workspace_bytes ? 1 : 0;
-    std::vector<int64_t> oks(world);
-    rc = dj_comm_allgather_i64(comm, &ok, 1, oks.data(), st);
+    if (t == 1) need += side_ws_bytes(max_span[0], plan, nseg) + side_ws_bytes(max_span[1], plan, nseg) + 4096;
+    rc = agree_fits(need);
     if (rc) return rc;
-    for (int r = 0; r < world; r++)
-      if (!oks[r]) {
-        set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
-                  "(this rank needs %zu of %zu bytes)", r, need, workspace_bytes);
+    for (int b = 0; b < odf; b++) {
+      const size_t i  = (size_t)b * 2 + t;
+      Piece& pc       = pieces[i];
+      pc.key          = arena.take<int64_t>((size_t)pc.span + 8);
+      pc.pay          = arena.take<int64_t>((size_t)pc.span + 8);
+      pc.d_seg_begin  = arena.take<int64_t>((size_t)nseg);
+      pc.d_seg_end    = arena.take<int64_t>((size_t)nseg);
+      pc.d_seg_parent = arena.take<int>((size_t)nseg);
+      if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) {
+        if (exchange_in_flight) cudaStreamSynchronize(comm->comm_stream);
+        set_error("distributed_inner_join: workspace too small for receive buffers");
         return DJ_ERR_WORKSPACE;
       }
-  }
-  int64_t* hseg = comm->h_pinned + (512 << 10);  // pinned staging for the segment tables
-  DJ_REQUIRE(pieces.size() * 3 * (size_t)nseg <= (512u << 10), "distributed_inner_join: too many segments");
-  for (size_t i = 0; i < pieces.size(); i++) {
-    Piece& pc       = pieces[i];
-    const int b     = (int)(i / 2), t = (int)(i % 2);
-    pc.key          = arena.take<int64_t>((size_t)pc.span + 8);
-    pc.pay          = arena.take<int64_t>((size_t)pc.span + 8);
-    pc.d_seg_begin  = arena.take<int64_t>((size_t)nseg);
-    pc.d_seg_end    = arena.take<int64_t>((size_t)nseg);
-    pc.d_seg_parent = arena.take<int>((size_t)nseg);
-    if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) {
-      set_error("distributed_inner_join: workspace too small for receive buffers");
-      return DJ_ERR_WORKSPACE;
-    }
-    int64_t* hb = hseg + i * 3 * nseg;
-    int* hpar   = reinterpret_cast<int*>(hb + 2 * (size_t)nseg);
-    for (int s = 0; s < G; s++) {
-      int64_t at = pc.begin[s];
-      for (int sub = 0; sub < F1s; sub++) {
-        const int64_t c       = cnt(s, t, b * G + rank, sub);
-        hb[s * F1s + sub]        = at;
-        hb[nseg + s * F1s + sub] = at + c;
-        hpar[s * F1s + sub]      = sub;
-        at += c;
+      int64_t* hb = hseg + i * 3 * nseg;
+      int* hpar   = reinterpret_cast<int*>(hb + 2 * (size_t)nseg);
+      for (int s = 0; s < G; s++) {
+        int64_t at = pc.begin[s];
+        for (int sub = 0; sub < F1s; sub++) {
+          const int64_t c          = cnt(s, t, b * G + rank, sub);
+          hb[s * F1s + sub]        = at;
+          hb[nseg + s * F1s + sub] = at + c;
+          hpar[s * F1s + sub]      = sub;
+          at += c;
+        }
       }
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_begin, hb, (size_t)nseg * 8, cudaMemcpyHostToDevice, comm->ctrl_stream));
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_end, hb + nseg, (size_t)nseg * 8, cudaMemcpyHostToDevice, comm->ctrl_stream));
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_parent, hpar, (size_t)nseg * 4, cudaMemcpyHostToDevice, comm->ctrl_stream));
     }
-    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_begin, hb, (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
-    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_end, hb + nseg, (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
-    DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_parent, hpar, (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
-  }
+    DJ_CUDA_TRY(cudaEventRecord(comm->ev_seg[t], comm->ctrl_stream));
 
-  // ---- 4. exchange table by table and batch by batch on the communicator's stream; an event
-  //         per (batch, table) hands the piece to the compute stream, so the radix pass of one
-  //         table overlaps the exchange of the next and batch b+1's exchange overlaps batch b's join
-  DJ_CUDA_TRY(cudaEventRecord(comm->ev_ready, st));
-  DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_ready, 0));
-  auto tcomm = std::chrono::high_resolution_clock::now();
-  for (int b = 0; b < odf; b++)
-    for (int t = 0; t < 2; t++) {
-      Piece& pc = pieces[(size_t)b * 2 + t];
-      auto send_begin = [&](int dest) { return off[t][((size_t)b * G + dest) << sub_bits]; };
-      auto send_count = [&](int dest) {
-        int64_t c = 0;
-        for (int sub = 0; sub < F1s; sub++) c += cntv[t][(((size_t)b * G + dest) << sub_bits) + sub];
-        return c;
-      };
-      // own bucket: device copy (src/all_to_all_comm.cpp:610-653); the rest over NVLink
-      if (pc.count[rank] > 0) {
-        DJ_CUDA_TRY(cudaMemcpyAsync(pc.key + pc.begin[rank], pk[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
-                                    cudaMemcpyDeviceToDevice, comm->comm_stream));
-        DJ_CUDA_TRY(cudaMemcpyAsync(pc.pay + pc.begin[rank], pp[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
-                                    cudaMemcpyDeviceToDevice, comm->comm_stream));
-      }
-      DJ_NCCL_TRY(ncclGroupStart());
-      for (int i = 0; i < G; i++) {
-        if (i == rank) continue;
-        const int64_t ns = send_count(i), nr = pc.count[i];
-        if (ns > 0) {
-          DJ_NCCL_TRY(ncclSend(pk[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
-          DJ_NCCL_TRY(ncclSend(pp[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
-          if (opts) opts->bytes_sent += 16 * ns;
+    // exchanges in batch order (b,L),(b,R); what can start now: (0,L) after the left table's
+    // sizes, everything else once the right table's sizes are known
+    DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_part[t], 0));
+    if (t == 0) {
+      rc = issue_exchange(0, 0);
+      if (rc) return rc;
+    } else {
+      rc = issue_exchange(0, 1);
+      if (rc) return rc;
+      for (int b = 1; b < odf; b++)
+        for (int tt = 0; tt < 2; tt++) {
+          rc = issue_exchange(b, tt);
+          if (rc) return rc;
         }
-        if (nr > 0) {
-          DJ_NCCL_TRY(ncclRecv(pc.key + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
-          DJ_NCCL_TRY(ncclRecv(pc.pay + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
-        }
-      }
-      DJ_NCCL_TRY(ncclGroupEnd());
-      DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[(size_t)b * 2 + t], comm->comm_stream));
     }
+  }
   if (timing) {
     DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
     opts->t_comm_ms = ms_since(tcomm);
     for (int b = 0; b < odf; b++)
       printf("Rank %d: All-to-all communication on batch %d takes %.0fms\n", rank, b, opts->t_comm_ms / odf);
   }
+  DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_seg[0], 0));
+  DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_seg[1], 0));
 
   const size_t join_mark = arena.used;
   for (int b = 0; b < odf; b++) {
@@ -544,7 +608,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   {
     int64_t over = *h_out_count > out_capacity ? 1 : 0;
     std::vector<int64_t> overs(world);
-    rc = dj_comm_allgather_i64(comm, &over, 1, overs.data(), st);
+    rc = ctrl_allgather(comm, &over, 1, overs.data());
     if (rc) return rc;
     for (int r = 0; r < world; r++)
       if (overs[r]) {

@@ -36,7 +36,9 @@ void count_launch(int n = 1);
     }                              \
   } while (0)
 
-int sm_count();
+int sm_count();           // SMs persistent kernels size their grids for (physical - reserve)
+int sm_count_physical();
+void set_sm_reserve(int n);
 
 // Brackets one kernel launch with CUDA events when profiling is enabled (dj_profile_enable).
 struct ProfScope {

@@ -45,6 +45,7 @@ struct PassDev {
   int S, P, F;
   uint32_t seed;
   int hash_id, shift, pow2;
+  int debug_linear;      // experiments only: write tiles back contiguously (wrong result)
   int nparts, sub_bits;  // mode 2: bucket = (row_hash % nparts) << sub_bits | top sub_bits of local_hash
 };
 
@@ -81,8 +82,8 @@ __device__ __forceinline__ int find_parent(const int* prefix, int P, int t)
 // parent offsets (segment i = parent i), or are the single range [0, nrows).
 __global__ void plan_kernel(const int64_t* parent_off_in, const int64_t* seg_begin_in,
                             const int64_t* seg_end_in, const int* seg_parent_in, int64_t nrows, int S,
-                            int64_t* seg_begin, int64_t* seg_end, int* seg_parent, int* hist_tiles,
-                            int* scat_tiles)
+                            int scatter_tile, int64_t* seg_begin, int64_t* seg_end, int* seg_parent,
+                            int* hist_tiles, int* scat_tiles)
 {
   __shared__ int warp_sums[33];
   const int tid = threadIdx.x;
@@ -107,7 +108,7 @@ __global__ void plan_kernel(const int64_t* parent_off_in, const int64_t* seg_beg
   }
   int64_t n = hi - lo;
   int ht    = (int)((n + kHistTileRows - 1) / kHistTileRows);
-  int st    = (int)((n + kScatterTile - 1) / kScatterTile);
+  int st    = (int)((n + scatter_tile - 1) / scatter_tile);
   int he = block_exclusive_scan<1024>(ht, warp_sums);
   if (tid < S) hist_tiles[tid] = he;
   if (tid == 0) hist_tiles[S] = warp_sums[32];
@@ -336,20 +337,22 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(PassDev d)
 // so the ranking / sorting phases never wait on global loads and HBM stays busy while they
 // run; everything else follows scatter_kernel.  Destination rows are tracked as 32-bit
 // offsets (tables < 2^32 rows).
-constexpr int kTmaThreads = 1024;
-constexpr int kTmaRows    = kScatterTile / kTmaThreads;  // rows per thread and tile
-
 struct TileDesc {
   int64_t beg;
   int n;
   int parent;
 };
 
+// THREADS x RPT rows per tile, two TMA stages.  RECOMPUTE drops the per-row bucket array of the
+// sorted tile and re-hashes the key when streaming it out (fewer shared-memory wavefronts, more
+// instructions).
+template <int THREADS, int RPT, bool RECOMPUTE>
 struct __align__(128) ScatterTmaSmem {
-  int64_t kst[2][kScatterTile + 2];
-  int64_t pst[2][kScatterTile + 2];
-  int4 srow[kScatterTile];
-  uint16_t sbkt[kScatterTile];
+  static constexpr int T = THREADS * RPT;
+  int64_t kst[2][T + 2];
+  int64_t pst[2][T + 2];
+  int4 srow[T];
+  uint16_t sbkt[RECOMPUTE ? 8 : T];
   int s_start[kMaxFanout];
   uint32_t s_delta[kMaxFanout];
   unsigned long long full[2];
@@ -357,12 +360,14 @@ struct __align__(128) ScatterTmaSmem {
   int warp_sums[33];
 };
 
-template <int MODE, bool WARP_AGG>
-__global__ void __launch_bounds__(kTmaThreads, 1) scatter_tma_kernel(PassDev d)
+template <int MODE, bool WARP_AGG, int THREADS, int RPT, bool RECOMPUTE>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2 > 1 ? 2 : 1) scatter_tma_kernel(PassDev d)
 {
+  using Smem = ScatterTmaSmem<THREADS, RPT, RECOMPUTE>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  ScatterTmaSmem& s = *reinterpret_cast<ScatterTmaSmem*>(smem_raw);
-  constexpr int T   = kScatterTile;
+  Smem& s           = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr int T   = THREADS * RPT;
+  constexpr int BPT = (kMaxFanout + THREADS - 1) / THREADS;  // histogram bins per thread
   const int tid     = threadIdx.x;
   const int lane    = tid & 31;
   const int F       = d.F;
@@ -396,7 +401,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) scatter_tma_kernel(PassDev d)
 
   for (int k = 0; blockIdx.x + k * (int)gridDim.x < total; k++) {
     const int st = k & 1;
-    if (tid < F) s.s_start[tid] = 0;
+#pragma unroll
+    for (int q = 0; q < BPT; q++)
+      if (tid + q * THREADS < F) s.s_start[tid + q * THREADS] = 0;
     __syncthreads();  // previous tile fully written out; descriptors of this tile visible
     mbar_wait(&s.full[st], (k >> 1) & 1);
     const TileDesc td  = s.desc[st];
@@ -405,16 +412,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1) scatter_tma_kernel(PassDev d)
     const int64_t* pst = s.pst[st] + skip_of(d.in_pay[0] + td.beg);
 
     // phase 1: keys from the staged tile -> bucket, rank inside the tile's bucket
-    int64_t key[kTmaRows];
-    uint32_t brank[kTmaRows];
+    int64_t key[RPT];
+    uint32_t brank[RPT];
 #pragma unroll
-    for (int j = 0; j < kTmaRows; j++) {
-      const int r = j * kTmaThreads + tid;
+    for (int j = 0; j < RPT; j++) {
+      const int r = j * THREADS + tid;
       key[j]      = r < tile_n ? kst[r] : 0;
     }
 #pragma unroll
-    for (int j = 0; j < kTmaRows; j++) {
-      const int r      = j * kTmaThreads + tid;
+    for (int j = 0; j < RPT; j++) {
+      const int r      = j * THREADS + tid;
       const bool valid = r < tile_n;
       const int b      = valid ? bucket_of<MODE>(key[j], d) : 0;
       int rank;
@@ -436,64 +443,307 @@ __global__ void __launch_bounds__(kTmaThreads, 1) scatter_tma_kernel(PassDev d)
     }
     __syncthreads();
 
-    // phase 2: exclusive scan of the tile histogram (one bin per thread); reserve the tile's
-    // slice of every bucket -- the atomicAdd results are consumed after phase 3
-    const int cnt = tid < F ? s.s_start[tid] : 0;
-    const int run = block_exclusive_scan<kTmaThreads>(cnt, s.warp_sums);
-    unsigned long long gres = 0;
-    if (tid < F) {
-      s.s_start[tid] = run;
-      if (cnt) gres = atomicAdd(&d.cursor[(size_t)td.parent * F + tid], (unsigned long long)cnt);
+    // phase 2: exclusive scan of the tile histogram (BPT consecutive bins per thread); reserve
+    // the tile's slice of every bucket -- the atomicAdd results are consumed after phase 3
+    int cnt[BPT], run[BPT];
+    unsigned long long gres[BPT];
+    {
+      int sum = 0;
+#pragma unroll
+      for (int q = 0; q < BPT; q++) {
+        const int bin = tid * BPT + q;
+        cnt[q]        = bin < F ? s.s_start[bin] : 0;
+        sum += cnt[q];
+      }
+      int excl = block_exclusive_scan<THREADS>(sum, s.warp_sums);
+#pragma unroll
+      for (int q = 0; q < BPT; q++) {
+        const int bin = tid * BPT + q;
+        run[q]        = excl;
+        gres[q]       = 0;
+        if (bin < F) {
+          s.s_start[bin] = excl;
+          if (cnt[q]) gres[q] = atomicAdd(&d.cursor[(size_t)td.parent * F + bin], (unsigned long long)cnt[q]);
+        }
+        excl += cnt[q];
+      }
     }
     __syncthreads();
 
     // phase 3: rows into bucket-sorted order (16-byte rows) in shared memory
 #pragma unroll
-    for (int j = 0; j < kTmaRows; j++) {
-      const int r = j * kTmaThreads + tid;
+    for (int j = 0; j < RPT; j++) {
+      const int r = j * THREADS + tid;
       if (r < tile_n) {
         const int b       = brank[j] >> 16;
         const int pos     = s.s_start[b] + (int)(brank[j] & 0xffffu);
         const int64_t pay = pst[r];
         s.srow[pos] = make_int4((int)(uint32_t)(uint64_t)key[j], (int)((uint64_t)key[j] >> 32),
                                 (int)(uint32_t)(uint64_t)pay, (int)((uint64_t)pay >> 32));
-        s.sbkt[pos] = (uint16_t)b;
+        if (!RECOMPUTE) s.sbkt[pos] = (uint16_t)b;
       }
     }
-    if (tid < F && cnt) s.s_delta[tid] = (uint32_t)gres - (uint32_t)run;
+#pragma unroll
+    for (int q = 0; q < BPT; q++)
+      if (cnt[q]) s.s_delta[tid * BPT + q] = (uint32_t)gres[q] - (uint32_t)run[q];
     __syncthreads();  // sorted tile complete; the input stage is free again
 
     if (tid == 0) issue_tile(k + 2);
 
     // phase 4: stream the sorted tile out; consecutive threads hit consecutive addresses
 #pragma unroll
-    for (int j = 0; j < kTmaRows; j++) {
-      const int i = j * kTmaThreads + tid;
+    for (int j = 0; j < RPT; j++) {
+      const int i = j * THREADS + tid;
       if (i < tile_n) {
         int4 row;
         asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(row.x), "=r"(row.y), "=r"(row.z), "=r"(row.w)
                      : "r"(smem_u32(&s.srow[i])));
-        const uint32_t dst   = s.s_delta[s.sbkt[i]] + (uint32_t)i;
-        d.out_key[dst]    = (int64_t)(((uint64_t)(uint32_t)row.y << 32) | (uint32_t)row.x);
-        d.out_pay[0][dst] = (int64_t)(((uint64_t)(uint32_t)row.w << 32) | (uint32_t)row.z);
+        const int64_t k64  = (int64_t)(((uint64_t)(uint32_t)row.y << 32) | (uint32_t)row.x);
+        const int b        = RECOMPUTE ? bucket_of<MODE>(k64, d) : (int)s.sbkt[i];
+        uint32_t dst = s.s_delta[b] + (uint32_t)i;
+        if (d.debug_linear) dst = (uint32_t)(td.beg + i);
+        d.out_key[dst]     = k64;
+        d.out_pay[0][dst]  = (int64_t)(((uint64_t)(uint32_t)row.w << 32) | (uint32_t)row.z);
       }
     }
   }
 }
 
-template <int MODE, bool AGG>
-int launch_scatter_tma(const PassDev& dev, cudaStream_t stream)
+// ---------------------------------------------------------------- scatter, TMA-staged, in place
+// Same algorithm with the tile sorted IN PLACE inside its single TMA stage: after ranking, the
+// payloads move to their sorted position inside the (already consumed) key array, then the keys
+// (held in registers) move into the payload array.  A CTA needs only 16 B/row of shared memory,
+// so tiles are larger (longer contiguous output runs) and 2-3 CTAs share an SM, hiding each
+// other's load latency and barrier phases.
+template <int THREADS, int RPT>
+struct __align__(128) ScatterInplaceSmem {
+  static constexpr int T = THREADS * RPT;
+  int64_t a[T + 2];  // TMA: keys            -> after the sort: payloads in bucket order
+  int64_t b[T + 2];  // TMA: payloads        -> after the sort: keys in bucket order
+  int s_start[kMaxFanout];
+  uint32_t s_delta[kMaxFanout];
+  unsigned long long full;
+  TileDesc desc;
+  int warp_sums[33];
+};
+
+template <int MODE, bool WARP_AGG, int THREADS, int RPT, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) scatter_inplace_kernel(PassDev d)
 {
-  const size_t smem = sizeof(ScatterTmaSmem);
-  auto kern         = scatter_tma_kernel<MODE, AGG>;
+  using Smem = ScatterInplaceSmem<THREADS, RPT>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& s           = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr int T   = THREADS * RPT;
+  constexpr int BPT = (kMaxFanout + THREADS - 1) / THREADS;
+  const int tid     = threadIdx.x;
+  const int lane    = tid & 31;
+  const int F       = d.F;
+  const int total   = d.scat_tiles[d.S];
+
+  int prod_parent = 0;
+  auto issue_tile = [&](int k) {  // thread 0 only
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= total) return;
+    while (d.scat_tiles[prod_parent + 1] <= t) prod_parent++;
+    const int64_t beg = d.seg_begin[prod_parent] + (int64_t)(t - d.scat_tiles[prod_parent]) * T;
+    int64_t end       = beg + T;
+    if (end > d.seg_end[prod_parent]) end = d.seg_end[prod_parent];
+    s.desc          = TileDesc{beg, (int)(end - beg), d.seg_parent[prod_parent]};
+    const Window wk = window_of(d.in_key + beg, (int)(end - beg));
+    const Window wp = window_of(d.in_pay[0] + beg, (int)(end - beg));
+    mbar_expect_tx(&s.full, wk.bytes + wp.bytes);
+    tma_load(s.a, wk.base, wk.bytes, &s.full);
+    tma_load(s.b, wp.base, wp.bytes, &s.full);
+  };
+
+  if (tid == 0) {
+    mbar_init(&s.full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue_tile(0);
+  }
+
+  for (int k = 0; blockIdx.x + k * (int)gridDim.x < total; k++) {
+#pragma unroll
+    for (int q = 0; q < BPT; q++)
+      if (tid + q * THREADS < F) s.s_start[tid + q * THREADS] = 0;
+    __syncthreads();  // histogram cleared; this tile's descriptor visible
+    mbar_wait(&s.full, k & 1);
+    const TileDesc td = s.desc;
+    const int tile_n  = td.n;
+    const int ska = skip_of(d.in_key + td.beg), skb = skip_of(d.in_pay[0] + td.beg);
+
+    // phase 1: keys -> bucket, rank inside the tile's bucket
+    int64_t key[RPT];
+    uint32_t brank[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+      const int r = j * THREADS + tid;
+      key[j]      = r < tile_n ? s.a[ska + r] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+      const int r      = j * THREADS + tid;
+      const bool valid = r < tile_n;
+      const int b      = valid ? bucket_of<MODE>(key[j], d) : 0;
+      int rank;
+      if (WARP_AGG) {
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        rank                 = 0;
+        if (valid) {
+          const unsigned peers = __match_any_sync(vmask, b);
+          const int leader     = __ffs(peers) - 1;
+          int base             = 0;
+          if (lane == leader) base = atomicAdd(&s.s_start[b], __popc(peers));
+          base = __shfl_sync(peers, base, leader);
+          rank = base + __popc(peers & lanemask_lt());
+        }
+      } else {
+        rank = valid ? atomicAdd(&s.s_start[b], 1) : 0;
+      }
+      brank[j] = ((uint32_t)b << 16) | (uint32_t)rank;
+    }
+    __syncthreads();  // histogram complete; every key is in registers: array `a` is free
+
+    // phase 2: exclusive scan (BPT consecutive bins per thread) + global slice reservation
+    int cnt[BPT], run[BPT];
+    unsigned long long gres[BPT];
+    {
+      int sum = 0;
+#pragma unroll
+      for (int q = 0; q < BPT; q++) {
+        const int bin = tid * BPT + q;
+        cnt[q]        = bin < F ? s.s_start[bin] : 0;
+        sum += cnt[q];
+      }
+      int excl = block_exclusive_scan<THREADS>(sum, s.warp_sums);
+#pragma unroll
+      for (int q = 0; q < BPT; q++) {
+        const int bin = tid * BPT + q;
+        run[q]        = excl;
+        gres[q]       = 0;
+        if (bin < F) {
+          s.s_start[bin] = excl;
+          if (cnt[q]) gres[q] = atomicAdd(&d.cursor[(size_t)td.parent * F + bin], (unsigned long long)cnt[q]);
+        }
+        excl += cnt[q];
+      }
+    }
+    __syncthreads();
+
+    // phase 3a: payloads to their sorted position inside array `a` (8 rows in flight per thread)
+    // (positions are kept in brank: bucket << 16 | position does not fit, so recompute start)
+    // (brank turns into the sorted position; 4 payloads in flight per thread keep registers low)
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+      const int r = j * THREADS + tid;
+      brank[j]    = r < tile_n ? (uint32_t)(s.s_start[brank[j] >> 16] + (int)(brank[j] & 0xffffu)) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < RPT; j0 += 4) {
+      int64_t pay[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int r = (j0 + j) * THREADS + tid;
+        pay[j]      = (j0 + j < RPT && r < tile_n) ? s.b[skb + r] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (j0 + j < RPT && brank[j0 + j] != 0xffffffffu) s.a[brank[j0 + j]] = pay[j];
+    }
+#pragma unroll
+    for (int q = 0; q < BPT; q++)
+      if (cnt[q]) s.s_delta[tid * BPT + q] = (uint32_t)gres[q] - (uint32_t)run[q];
+    __syncthreads();  // every payload has left array `b`
+    // phase 3b: keys (registers) to their sorted position inside array `b`
+#pragma unroll
+    for (int j = 0; j < RPT; j++)
+      if (brank[j] != 0xffffffffu) s.b[brank[j]] = key[j];
+    __syncthreads();
+
+    // phase 4: stream the sorted tile out; the bucket is recomputed from the key
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+      const int i = j * THREADS + tid;
+      if (i < tile_n) {
+        const int64_t k64 = s.b[i];
+        const int64_t p64 = s.a[i];
+        uint32_t dst      = s.s_delta[bucket_of<MODE>(k64, d)] + (uint32_t)i;
+        if (d.debug_linear) dst = (uint32_t)(td.beg + i);
+        d.out_key[dst]    = k64;
+        d.out_pay[0][dst] = p64;
+      }
+    }
+    __syncthreads();  // stage fully drained: refill it
+    if (tid == 0) issue_tile(k + 1);
+  }
+}
+
+// Kernel shape, selectable for experiments with DJ_SCATTER_CFG:
+//   0: 1024 threads x 4 rows, 1 CTA/SM        1: 512 x 4, 2 CTAs/SM
+//   2: like 0, bucket recomputed on write-out  3: like 1, bucket recomputed on write-out
+//   4: in place, 512 x 12 rows, 2 CTAs/SM     5: in place, 512 x 8 rows, 3 CTAs/SM
+//   6: in place, 1024 x 8 rows, 1 CTA/SM
+int scatter_cfg()
+{
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DJ_SCATTER_CFG");
+    v             = e ? atoi(e) : 0;
+    if (v < 0 || v > 6) v = 0;
+  }
+  return v;
+}
+int scatter_tile_rows()
+{
+  switch (scatter_cfg()) {
+    case 1: case 3: return 2048;
+    case 4: return 6144;
+    case 6: return 8192;
+    default: return 4096;
+  }
+}
+
+template <int MODE, bool AGG, int THREADS, int RPT, bool RECOMPUTE>
+int launch_scatter_tma_cfg(const PassDev& dev, int ctas_per_sm, cudaStream_t stream)
+{
+  const size_t smem = sizeof(ScatterTmaSmem<THREADS, RPT, RECOMPUTE>);
+  auto kern         = scatter_tma_kernel<MODE, AGG, THREADS, RPT, RECOMPUTE>;
   DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope prof(DJ_PROF_SCATTER, stream);
-    kern<<<sm_count(), kTmaThreads, smem, stream>>>(dev);
+    kern<<<sm_count() * ctas_per_sm, THREADS, smem, stream>>>(dev);
   }
   DJ_LAUNCH_CHECK();
   return DJ_OK;
+}
+
+template <int MODE, bool AGG, int THREADS, int RPT, int CTAS>
+int launch_scatter_inplace(const PassDev& dev, cudaStream_t stream)
+{
+  const size_t smem = sizeof(ScatterInplaceSmem<THREADS, RPT>);
+  auto kern         = scatter_inplace_kernel<MODE, AGG, THREADS, RPT, CTAS>;
+  DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof(DJ_PROF_SCATTER, stream);
+    kern<<<sm_count() * CTAS, THREADS, smem, stream>>>(dev);
+  }
+  DJ_LAUNCH_CHECK();
+  return DJ_OK;
+}
+
+template <int MODE, bool AGG>
+int launch_scatter_tma(const PassDev& dev, cudaStream_t stream)
+{
+  switch (scatter_cfg()) {
+    case 4: return launch_scatter_inplace<MODE, AGG, 512, 12, 2>(dev, stream);
+    case 5: return launch_scatter_inplace<MODE, AGG, 512, 8, 3>(dev, stream);
+    case 6: return launch_scatter_inplace<MODE, AGG, 1024, 8, 1>(dev, stream);
+    case 1: return launch_scatter_tma_cfg<MODE, AGG, 512, 4, false>(dev, 2, stream);
+    case 2: return launch_scatter_tma_cfg<MODE, AGG, 1024, 4, true>(dev, 1, stream);
+    case 3: return launch_scatter_tma_cfg<MODE, AGG, 512, 4, true>(dev, 2, stream);
+    default: return launch_scatter_tma_cfg<MODE, AGG, 1024, 4, false>(dev, 1, stream);
+  }
 }
 
 bool use_tma_scatter()
@@ -604,8 +854,12 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   }
 
   DJ_CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 1) * 8, stream));
+  // 32-bit destination offsets in the TMA kernel: input rows + worst-case padding must fit
+  const int64_t span = buf.nrows + (int64_t)nb * desc.align_rows;
+  const bool tma     = desc.npay == 1 && span < ((int64_t)1 << 32) && use_tma_scatter();
   plan_kernel<<<1, 1024, 0, stream>>>(buf.d_parent_off, buf.d_seg_begin, buf.d_seg_end, buf.d_seg_parent,
-                                      buf.nrows, S, seg_begin, seg_end, seg_parent, hist_tiles, scat_tiles);
+                                      buf.nrows, S, tma ? scatter_tile_rows() : kScatterTile, seg_begin,
+                                      seg_end, seg_parent, hist_tiles, scat_tiles);
   DJ_LAUNCH_CHECK();
 
   PassDev dev{};
@@ -630,6 +884,10 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   dev.shift      = desc.shift;
   dev.pow2       = desc.mode == 2 ? (desc.nparts & (desc.nparts - 1)) == 0 : (desc.F & (desc.F - 1)) == 0;
   dev.nparts     = desc.nparts;
+  {
+    const char* e    = getenv("DJ_SCATTER_DEBUG_LINEAR");
+    dev.debug_linear = e && e[0] == '1';
+  }
   dev.sub_bits   = desc.sub_bits;
 
   const int hist_grid = sm_count() * 4;
@@ -660,8 +918,6 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
     DJ_CUDA_TRY(cudaMemcpyAsync(cursor, buf.d_child_off, nb * 8, cudaMemcpyDeviceToDevice, stream));
   }
 
-  // 32-bit destination offsets in the TMA kernel: input rows + worst-case padding must fit
-  const int64_t span = buf.nrows + (int64_t)nb * desc.align_rows;
   if (desc.mode == 0) return launch_scatter_npay<0>(dev, desc.npay, desc.F, span, stream);
   if (desc.mode == 1) return launch_scatter_npay<1>(dev, desc.npay, desc.F, span, stream);
   return launch_scatter_npay<2>(dev, desc.npay, desc.F, span, stream);

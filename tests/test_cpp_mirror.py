@@ -26,6 +26,31 @@ def test_cpp_headers_mirror_reference_names():
         assert name in text, name
 
 
+def test_communication_group_semantics():
+    """CPU: CommunicationGroup(grid, stride) membership, the reference's documented example
+    (src/all_to_all_comm.hpp:72-113): 16 ranks, grid 8, stride 2 -> {0,2,4,6} {1,3,5,7} {8,10,12,14} {9,11,13,15}."""
+    exe = os.path.join(BIN, "test_comm_group")
+    if not os.path.exists(exe):
+        pytest.skip("bin/test_comm_group not built")
+
+    def group(rank, grid, stride):
+        out = subprocess.run([exe, str(grid), str(stride)], env=dict(os.environ, RANK=str(rank), WORLD_SIZE="16"),
+                             capture_output=True, text=True, check=True).stdout.split()
+        return int(out[0]), int(out[1]), [int(x) for x in out[2:]]
+
+    want = {0: [0, 2, 4, 6], 1: [1, 3, 5, 7], 8: [8, 10, 12, 14], 9: [9, 11, 13, 15]}
+    for rank in range(16):
+        size, idx, members = group(rank, 8, 2)
+        head = rank // 8 * 8 + rank % 2
+        assert size == 4 and members == want[head] and members[idx] == rank
+    # stride 1 over all ranks (what shuffle_on / the NVLink stage use)
+    size, idx, members = group(5, 16, 1)
+    assert size == 16 and idx == 5 and members == list(range(16))
+    # the IB-stage group of distributed_inner_join: CommunicationGroup(N, G) with N=8, G=2
+    size, idx, members = group(5, 8, 2)
+    assert members == [1, 3, 5, 7] and idx == 2
+
+
 def _run(nproc, exe, *args):
     if nproc == 1:
         return subprocess.run([os.path.join(BIN, exe), *args], cwd=ROOT, capture_output=True, text=True, timeout=300,
