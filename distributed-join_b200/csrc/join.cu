@@ -19,6 +19,9 @@
 //                      stores; the atomic's round trip is hidden behind the next round of probing
 //                      (three tiles rotate), and batch results land in one output so no
 //                      cudf::concatenate is needed afterwards.
+// Tried and rejected (measured on B200, 800M x 800M): replacing the two consumer bar.sync phases by
+// split arrive/wait mbarriers so that early warps start the next table's inserts -- 16.0 -> 20.0 ms
+// (inserts then contend with probes for the atomic unit and the mbarrier polls cost issue slots).
 // Multimap semantics: probing continues past a hit until an empty slot.  Build buckets larger
 // than one chunk (skew / duplicates) are processed chunk by chunk, re-streaming the probe side.
 #include <cstdlib>
@@ -75,7 +78,6 @@ struct __align__(128) JoinSmem {
   int64_t dpoff[kDescBuckets + 1];
   unsigned long long full_build[2], empty_build[2];
   unsigned long long full_probe[C::kProbeStages], empty_probe[C::kProbeStages];
-  unsigned long long mb_built, mb_probed;  // consumer-only phase barriers (split arrive / wait)
   unsigned long long sbase[kOutTiles];
   int scnt[kOutTiles];
 };
@@ -119,8 +121,6 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
       mbar_init(&s.full_probe[i], 1);
       mbar_init(&s.empty_probe[i], C::kConsWarps);
     }
-    mbar_init(&s.mb_built, C::kConsWarps);
-    mbar_init(&s.mb_probed, C::kConsWarps);
     for (int i = 0; i < kOutTiles; i++) s.scnt[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,10 +183,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
         const int64_t b1 = s.dboff[lb + 1], p0 = s.dpoff[lb], p1 = s.dpoff[lb + 1];
         for (int64_t c0 = s.dboff[lb]; c0 < b1; c0 += C::kBuildChunk) {
           // ---- build: fingerprint + row index into a 32-bit slot claimed with atomicCAS; the
-          //      staged rows themselves are the row store (no copy).  Phases are separated by
-          //      split arrive/wait mbarriers, so a warp that is done early starts the next phase's
-          //      independent work (inserting the next table, fetching its probe rows) instead of
-          //      idling at a CTA barrier behind the slowest warp.
+          //      staged rows themselves are the row store (no copy)
           const int bs = u & 1;
           const int nb = (int)min((int64_t)C::kBuildChunk, b1 - c0);
           uint32_t* slots     = s.slots[bs];
@@ -199,39 +196,14 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
             uint32_t slot    = h & (C::kSlots - 1);
             while (atomicCAS(&slots[slot], 0u, e) != 0u) slot = (slot + 1) & (C::kSlots - 1);
           }
-          if (u > 0) {
-            // every warp has finished probing the previous table: release its row store, rotate
-            // the output tiles, and only then clear that table for the job after this one
-            mbar_wait(&s.mb_probed, (u - 1) & 1);
-            if (lane == 0) mbar_arrive(&s.empty_build[bs ^ 1]);
-            if (pend_n) {
-              // copy out the tile whose atomicAdd was issued one build job ago (latency hidden)
-              const int64_t gb = (int64_t)s.sbase[pend_tile];
-#pragma unroll
-              for (int c = 0; c < 4; c++)
-                for (int i = tid; i < pend_n; i += kConsumers)
-                  if (gb + i < d.out_capacity) d.out[c][gb + i] = s.sout[pend_tile][c][i];
-              if (tid == 0) s.scnt[pend_tile] = 0;
-              pend_n = 0;
-            }
-            int n_out = s.scnt[cur];
-            if (n_out > 0) {
-              if (n_out > C::kOutRows) n_out = C::kOutRows;
-              if (tid == 0) pend_base_reg = atomicAdd(d.out_count, (unsigned long long)n_out);
-              pend_n    = n_out;
-              pend_tile = cur;
-              cur       = cur + 1 == kOutTiles ? 0 : cur + 1;
-            }
-          }
+          // the other table was last probed two build jobs ago: clear it for the next job
           {
             uint4* other = reinterpret_cast<uint4*>(s.slots[bs ^ 1]);
             for (int i = tid; i < C::kSlots / 4; i += kConsumers) other[i] = make_uint4(0, 0, 0, 0);
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s.mb_built);  // this warp's inserts and clears are done
+          consumer_sync<kConsumers>();  // table complete
 
           // ---- probe: every warp streams its 32 rows of each staged chunk at its own pace
-          bool table_ready = false;
           for (int64_t r0 = p0; r0 < p1; r0 += C::kProbeChunk) {
             const int st = q % C::kProbeStages;
             const int np = (int)min((int64_t)C::kProbeChunk, p1 - r0);
@@ -249,10 +221,6 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
             const uint32_t h    = slot_hash_i64(k);
             const uint32_t want = slot_tag(h);
             uint32_t slot       = h & (C::kSlots - 1);
-            if (!table_ready) {
-              mbar_wait(&s.mb_built, u & 1);  // table complete (all warps inserted)
-              table_ready = true;
-            }
             while (true) {
               bool found = false;
               int idx    = 0;
@@ -309,38 +277,46 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
               if (found) slot = (slot + 1) & (C::kSlots - 1);  // multimap: scan past the hit
             }
           }
-          if (!table_ready) mbar_wait(&s.mb_built, u & 1);  // keep the barrier phases in step
 
-          // ---- end of this warp's share of the build job
-          if (tid == 0 && pend_n) s.sbase[pend_tile] = pend_base_reg;  // arrived long ago
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s.mb_probed);
+          // ---- end of build job: table and row store are released, output tiles rotate
+          if (tid == 0 && pend_n) s.sbase[pend_tile] = pend_base_reg;
+          consumer_sync<kConsumers>();
+          if (lane == 0) mbar_arrive(&s.empty_build[bs]);
+          if (pend_n) {
+            // copy out the tile whose atomicAdd was issued one build job ago (latency hidden);
+            // it stays untouched until the job after next, when every thread is past here
+            const int64_t gb = (int64_t)s.sbase[pend_tile];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+              for (int i = tid; i < pend_n; i += kConsumers)
+                if (gb + i < d.out_capacity) d.out[c][gb + i] = s.sout[pend_tile][c][i];
+            if (tid == 0) s.scnt[pend_tile] = 0;
+            pend_n = 0;
+          }
+          int n_out = s.scnt[cur];
+          if (n_out > 0) {
+            if (n_out > C::kOutRows) n_out = C::kOutRows;
+            if (tid == 0) pend_base_reg = atomicAdd(d.out_count, (unsigned long long)n_out);
+            pend_n    = n_out;
+            pend_tile = cur;
+            cur       = cur + 1 == kOutTiles ? 0 : cur + 1;
+          }
           u++;
         }
       }
     }
   }
 
-  // ---- drain: last job's bookkeeping, the pending tile, then the partially filled current tile
-  if (!is_producer && u > 0) {
-    mbar_wait(&s.mb_probed, (u - 1) & 1);
+  // ---- drain the pending tile (the current one is empty: every job hands its tile over)
+  if (!is_producer) {
+    if (tid == 0 && pend_n) s.sbase[pend_tile] = pend_base_reg;
+    consumer_sync<kConsumers>();
     if (pend_n) {
       const int64_t gb = (int64_t)s.sbase[pend_tile];
 #pragma unroll
       for (int c = 0; c < 4; c++)
         for (int i = tid; i < pend_n; i += kConsumers)
           if (gb + i < d.out_capacity) d.out[c][gb + i] = s.sout[pend_tile][c][i];
-    }
-    int n_out = s.scnt[cur];
-    if (n_out > C::kOutRows) n_out = C::kOutRows;
-    if (n_out > 0) {
-      if (tid == 0) s.sbase[cur] = atomicAdd(d.out_count, (unsigned long long)n_out);
-      consumer_sync<kConsumers>();
-      const int64_t gb = (int64_t)s.sbase[cur];
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        for (int i = tid; i < n_out; i += kConsumers)
-          if (gb + i < d.out_capacity) d.out[c][gb + i] = s.sout[cur][c][i];
     }
   }
 }
