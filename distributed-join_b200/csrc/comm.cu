@@ -9,6 +9,7 @@
 //   * the reference's spinning join thread + std::atomic flags (:100-132,283-322) become two
 //     CUDA streams and events: batch b+1's exchange overlaps batch b's local join;
 //   * batch results are appended into one output (no cudf::concatenate, :333-339).
+#include <cuda.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -32,6 +33,21 @@ struct dj_comm {
   cudaEvent_t ev_part[2]   = {nullptr, nullptr};
   cudaEvent_t ev_seg[2]    = {nullptr, nullptr};
   std::vector<cudaEvent_t> ev_batch;
+  // Peer-memory exchange (copy engines over NVLink, no SMs): every rank maps every peer's flag
+  // block and -- per call -- workspace through CUDA IPC, pushes its buckets with cudaMemcpyAsync
+  // and signals with a stream write; receivers wait with a stream wait-value.
+  bool peer_ok = false;
+  uint32_t* d_flags = nullptr;               // [size][kFlagSlots], written by peers
+  std::vector<uint32_t*> peer_flags;         // peers' d_flags mapped here
+  std::vector<cudaStream_t> peer_stream;     // one push stream per peer
+  struct IpcEntry { cudaIpcMemHandle_t h; char* base; };
+  std::vector<std::vector<IpcEntry>> ipc_cache;  // per peer: opened workspace allocations
+  uint32_t seq = 0;
+  bool flag_by_memcpy = false;
+  bool wait_flush = true;  // CU_STREAM_WAIT_VALUE_FLUSH is dropped if the driver refuses it  // fallback when stream write-value is refused on peer memory
+  CUresult (*fn_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*fn_write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*fn_addr_range)(CUdeviceptr*, size_t*, CUdeviceptr) = nullptr;
   int64_t* h_pinned = nullptr;  // pinned scratch
   int64_t* d_small  = nullptr;  // device scratch for tiny collectives
   size_t small_elems = 0;
@@ -48,6 +64,7 @@ namespace dj {
     }                                                                                         \
   } while (0)
 
+constexpr int kFlagSlots = 64;
 constexpr size_t kSmallElems = 1 << 20;  // int64 entries of pinned + device scratch per communicator
 
 static int ensure_events(dj_comm* c, int n)
@@ -63,6 +80,84 @@ static int ensure_events(dj_comm* c, int n)
 }  // namespace dj
 
 using namespace dj;
+
+static int ctrl_allgather(dj_comm* c, const int64_t* h_mine, int n, int64_t* h_all);
+
+// Maps every peer's flag block; decides (collectively) whether the copy-engine exchange is usable.
+static int setup_peer_exchange(dj_comm* c)
+{
+  const char* mode = getenv("DJ_EXCHANGE");
+  bool ok = !(mode && (mode[0] == 'n' || mode[0] == 'N'));  // DJ_EXCHANGE=nccl forces the NCCL path
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) ok = false;
+  c->fn_wait32 = (decltype(c->fn_wait32))fn;
+  fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) ok = false;
+  c->fn_write32 = (decltype(c->fn_write32))fn;
+  fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) ok = false;
+  c->fn_addr_range = (decltype(c->fn_addr_range))fn;
+  cudaGetLastError();
+
+  DJ_CUDA_TRY(cudaMalloc(&c->d_flags, (size_t)c->size * kFlagSlots * sizeof(uint32_t)));
+  DJ_CUDA_TRY(cudaMemset(c->d_flags, 0, (size_t)c->size * kFlagSlots * sizeof(uint32_t)));
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, c->d_flags) != cudaSuccess) {
+    ok = false;
+    memset(&mine, 0, sizeof(mine));
+    cudaGetLastError();
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  std::vector<int64_t> send(9), all((size_t)c->size * 9);
+  send[0] = ok ? 1 : 0;
+  memcpy(&send[1], &mine, 64);
+  int rc = ctrl_allgather(c, send.data(), 9, all.data());
+  if (rc) return rc;
+  for (int r = 0; r < c->size; r++) ok = ok && all[(size_t)r * 9] == 1;
+  c->peer_flags.assign(c->size, nullptr);
+  c->peer_stream.assign(c->size, nullptr);
+  c->ipc_cache.assign(c->size, {});
+  int64_t opened = 1;
+  if (ok) {
+    for (int r = 0; r < c->size; r++) {
+      if (r == c->rank) {
+        c->peer_flags[r] = c->d_flags;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &all[(size_t)r * 9 + 1], 64);
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        opened = 0;
+        cudaGetLastError();
+        break;
+      }
+      c->peer_flags[r] = (uint32_t*)p;
+      DJ_CUDA_TRY(cudaStreamCreateWithFlags(&c->peer_stream[r], cudaStreamNonBlocking));
+    }
+  }
+  std::vector<int64_t> oks(c->size);
+  rc = ctrl_allgather(c, &opened, 1, oks.data());
+  if (rc) return rc;
+  for (int r = 0; r < c->size; r++) ok = ok && oks[r] == 1;
+  c->peer_ok = ok;
+  return DJ_OK;
+}
+
+// Peer view of rank `peer`'s workspace allocation described by (handle, offset); opened once.
+static char* map_peer_workspace(dj_comm* c, int peer, const cudaIpcMemHandle_t& h, int64_t offset)
+{
+  for (auto& e : c->ipc_cache[peer])
+    if (memcmp(&e.h, &h, sizeof(h)) == 0) return e.base + offset;
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  c->ipc_cache[peer].push_back({h, (char*)p});
+  return (char*)p + offset;
+}
 
 extern "C" int dj_comm_unique_id(void* h_id128)
 {
@@ -97,6 +192,10 @@ extern "C" int dj_comm_create(int rank, int size, const void* h_id128, dj_comm_t
   DJ_CUDA_TRY(cudaMallocHost(&c->h_pinned, kSmallElems * sizeof(int64_t)));
   DJ_CUDA_TRY(cudaMalloc(&c->d_small, kSmallElems * sizeof(int64_t)));
   c->small_elems = kSmallElems;
+  if (size > 1) {
+    int rc = setup_peer_exchange(c);
+    if (rc) return rc;
+  }
   *out           = c;
   return DJ_OK;
 }
@@ -112,6 +211,13 @@ extern "C" int dj_comm_destroy(dj_comm_t* c)
     if (c->ev_seg[i]) cudaEventDestroy(c->ev_seg[i]);
   }
   if (c->ctrl_stream) cudaStreamDestroy(c->ctrl_stream);
+  for (auto ps : c->peer_stream)
+    if (ps) cudaStreamDestroy(ps);
+  for (int i = 0; i < (int)c->peer_flags.size(); i++)
+    if (c->peer_flags[i] && i != c->rank) cudaIpcCloseMemHandle(c->peer_flags[i]);
+  for (auto& v : c->ipc_cache)
+    for (auto& e : v) cudaIpcCloseMemHandle(e.base);
+  if (c->d_flags) cudaFree(c->d_flags);
   for (auto e : c->ev_batch) cudaEventDestroy(e);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -275,6 +381,42 @@ extern "C" size_t dj_distributed_inner_join_workspace_bytes(int64_t nleft, int64
   return dist_ws_bytes(nleft, nright, world, over_decom_factor < 1 ? 1 : over_decom_factor, 1.15);
 }
 
+// DJ_TRACE=1: device-side timeline of one call (CUDA event timestamps relative to its start)
+struct Trace {
+  bool on = false;
+  cudaEvent_t base = nullptr;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  void init(cudaStream_t st)
+  {
+    const char* e = getenv("DJ_TRACE");
+    on            = e && e[0] == '1';
+    if (!on) return;
+    cudaEventCreate(&base);
+    cudaEventRecord(base, st);
+  }
+  void mark(const char* name, cudaStream_t st)
+  {
+    if (!on) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    marks.push_back({name, ev});
+  }
+  void dump(int rank)
+  {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    for (auto& m : marks) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, base, m.second);
+      printf("[trace rank %d] %8.3f ms  %s\n", rank, ms, m.first);
+      cudaEventDestroy(m.second);
+    }
+    cudaEventDestroy(base);
+    fflush(stdout);
+  }
+};
+
 static double ms_since(std::chrono::high_resolution_clock::time_point t0)
 {
   return std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
@@ -337,6 +479,8 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
              "distributed_inner_join: per-rank tables are limited to 2^31 rows");
   int rc = ensure_events(comm, 2 * odf);
   if (rc) return rc;
+  Trace trace;
+  trace.init(st);
 
   // ---- 0. agree on the join's radix plan from the global table sizes.  When the plan has two
   //         levels, the first one is FUSED into the rank partition on the sender: bucket =
@@ -368,6 +512,43 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       }
     }
   }
+  // ---- 0b. copy-engine exchange: map every peer's workspace for this call (cached per allocation)
+  bool use_peer = comm->peer_ok && 2 * odf <= kFlagSlots;
+  std::vector<char*> peer_ws(world, nullptr);
+  if (use_peer) {
+    CUdeviceptr base = 0;
+    size_t alloc_sz  = 0;
+    cudaIpcMemHandle_t wh;
+    memset(&wh, 0, sizeof(wh));
+    bool ok = comm->fn_addr_range(&base, &alloc_sz, (CUdeviceptr)d_workspace) == CUDA_SUCCESS &&
+              cudaIpcGetMemHandle(&wh, (void*)base) == cudaSuccess;
+    cudaGetLastError();
+    std::vector<int64_t> send(10), allh((size_t)world * 10);
+    send[0] = ok ? 1 : 0;
+    send[1] = ok ? (int64_t)((CUdeviceptr)d_workspace - base) : 0;
+    memcpy(&send[2], &wh, 64);
+    rc = ctrl_allgather(comm, send.data(), 10, allh.data());
+    if (rc) return rc;
+    for (int r = 0; r < world; r++) ok = ok && allh[(size_t)r * 10] == 1;
+    int64_t mapped = 1;
+    if (ok)
+      for (int r = 0; r < world && mapped; r++) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &allh[(size_t)r * 10 + 2], 64);
+        peer_ws[r] = map_peer_workspace(comm, r, h, allh[(size_t)r * 10 + 1]);
+        if (!peer_ws[r]) mapped = 0;
+      }
+    std::vector<int64_t> oks(world);
+    rc = ctrl_allgather(comm, &mapped, 1, oks.data());
+    if (rc) return rc;
+    for (int r = 0; r < world; r++) ok = ok && oks[r] == 1;
+    use_peer = ok;  // identical on every rank; otherwise fall back to the NCCL exchange
+  }
+  const uint32_t seq = use_peer ? ++comm->seq : 0;
+  std::vector<int64_t> peer_piece_off;  // [table][rank][batch][key|pay] byte offsets in the peer's workspace
+  peer_piece_off.assign((size_t)2 * world * odf * 2, 0);
+
   const int F1s = 1 << sub_bits;       // sub-buckets per destination in the sender's partition
   const int nbk = nparts << sub_bits;  // buckets of the sender's partition
   const int nseg = G * F1s;            // (source, sub-bucket) segments of a received piece
@@ -404,6 +585,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     set_sm_reserve(0);
     if (rc) return rc;
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_part[t], st));
+    trace.mark(t ? "partition(R) done" : "partition(L) done", st);
   }
 
   // ---- 2-4. table by table: sizes (communicate_sizes, on the control communicator), receive
@@ -438,12 +620,52 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       for (int sub = 0; sub < F1s; sub++) c += cntv[t][(((size_t)b * G + dest) << sub_bits) + sub];
       return c;
     };
+    trace.mark(t ? "exchange(R) begin" : "exchange(L) begin", comm->comm_stream);
     // own bucket: device copy (src/all_to_all_comm.cpp:610-653); the rest over NVLink
     if (pc.count[rank] > 0) {
       DJ_CUDA_TRY(cudaMemcpyAsync(pc.key + pc.begin[rank], pk[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
                                   cudaMemcpyDeviceToDevice, comm->comm_stream));
       DJ_CUDA_TRY(cudaMemcpyAsync(pc.pay + pc.begin[rank], pp[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
                                   cudaMemcpyDeviceToDevice, comm->comm_stream));
+    }
+    if (use_peer) {
+      // push every peer's bucket into ITS receive piece with the copy engines (no SMs, so the
+      // radix passes running meanwhile keep the whole GPU), then raise that peer's flag
+      const int slot = (b * 2 + t) % kFlagSlots;
+      for (int i = 0; i < G; i++) {
+        if (i == rank) continue;
+        cudaStream_t ps = comm->peer_stream[i];
+        DJ_CUDA_TRY(cudaStreamWaitEvent(ps, comm->ev_part[t], 0));
+        const int64_t ns = send_count(i);
+        if (ns > 0) {
+          // where my rows start inside peer i's piece: padded counts of the sources before me
+          int64_t dst_begin = 0;
+          for (int s2 = 0; s2 < rank; s2++) {
+            int64_t c = 0;
+            for (int sub = 0; sub < F1s; sub++) c += cnt(s2, t, b * G + i, sub);
+            dst_begin += pad_rows(c);
+          }
+          const int64_t* po = &peer_piece_off[(((size_t)t * world + i) * odf + b) * 2];
+          DJ_CUDA_TRY(cudaMemcpyAsync(peer_ws[i] + po[0] + dst_begin * 8, pk[t] + send_begin(i), (size_t)ns * 8,
+                                      cudaMemcpyDefault, ps));
+          DJ_CUDA_TRY(cudaMemcpyAsync(peer_ws[i] + po[1] + dst_begin * 8, pp[t] + send_begin(i), (size_t)ns * 8,
+                                      cudaMemcpyDefault, ps));
+          if (opts) opts->bytes_sent += 16 * ns;
+        }
+        uint32_t* flag = comm->peer_flags[i] + (size_t)rank * kFlagSlots + slot;
+        if (!comm->flag_by_memcpy &&
+            comm->fn_write32((CUstream)ps, (CUdeviceptr)flag, seq, 0) != CUDA_SUCCESS)
+          comm->flag_by_memcpy = true;
+        if (comm->flag_by_memcpy) {
+          // 4-byte copy from a pinned word (ordered behind the data copies on the same stream)
+          uint32_t* src = reinterpret_cast<uint32_t*>(comm->h_pinned + (900 << 10)) + (seq % 4096);
+          *src          = seq;
+          DJ_CUDA_TRY(cudaMemcpyAsync(flag, src, 4, cudaMemcpyDefault, ps));
+        }
+      }
+      DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[(size_t)b * 2 + t], comm->comm_stream));
+      exchange_in_flight = true;
+      return DJ_OK;
     }
     DJ_NCCL_TRY(ncclGroupStart());
     for (int i = 0; i < G; i++) {
@@ -461,8 +683,16 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     }
     DJ_NCCL_TRY(ncclGroupEnd());
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[(size_t)b * 2 + t], comm->comm_stream));
+    trace.mark(t ? "exchange(R) end" : "exchange(L) end", comm->comm_stream);
     exchange_in_flight = true;
     return DJ_OK;
+  };
+  auto drain_exchange = [&]() {
+    if (!exchange_in_flight) return;
+    cudaStreamSynchronize(comm->comm_stream);
+    if (use_peer)
+      for (int i = 0; i < G; i++)
+        if (i != rank) cudaStreamSynchronize(comm->peer_stream[i]);
   };
   // collective verdict on the control communicator; drains the bulk stream before failing
   auto agree_fits = [&](size_t need) -> int {
@@ -472,7 +702,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     if (r2) return r2;
     for (int r = 0; r < world; r++)
       if (!oks[r]) {
-        if (exchange_in_flight) cudaStreamSynchronize(comm->comm_stream);
+        drain_exchange();
         set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
                   "(this rank needs %zu of %zu bytes)", r, need, workspace_bytes);
         return DJ_ERR_WORKSPACE;
@@ -527,7 +757,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       pc.d_seg_end    = arena.take<int64_t>((size_t)nseg);
       pc.d_seg_parent = arena.take<int>((size_t)nseg);
       if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) {
-        if (exchange_in_flight) cudaStreamSynchronize(comm->comm_stream);
+        drain_exchange();
         set_error("distributed_inner_join: workspace too small for receive buffers");
         return DJ_ERR_WORKSPACE;
       }
@@ -548,6 +778,18 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_parent, hpar, (size_t)nseg * 4, cudaMemcpyHostToDevice, comm->ctrl_stream));
     }
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_seg[t], comm->ctrl_stream));
+    if (use_peer) {
+      std::vector<int64_t> mine_off((size_t)odf * 2), all_off((size_t)world * odf * 2);
+      for (int b = 0; b < odf; b++) {
+        mine_off[(size_t)b * 2]     = (char*)pieces[(size_t)b * 2 + t].key - (char*)d_workspace;
+        mine_off[(size_t)b * 2 + 1] = (char*)pieces[(size_t)b * 2 + t].pay - (char*)d_workspace;
+      }
+      rc = ctrl_allgather(comm, mine_off.data(), odf * 2, all_off.data());
+      if (rc) return rc;
+      for (int r = 0; r < world; r++)
+        for (int k = 0; k < odf * 2; k++)
+          peer_piece_off[((size_t)t * world + r) * odf * 2 + k] = all_off[(size_t)r * odf * 2 + k];
+    }
 
     // exchanges in batch order (b,L),(b,R); what can start now: (0,L) after the left table's
     // sizes, everything else once the right table's sizes are known
@@ -586,12 +828,34 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     for (int t = 0; t < 2; t++) {
       Piece& pc = t ? R : L;
       DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_batch[(size_t)b * 2 + t], 0));
+      if (use_peer) {
+        const int slot = (b * 2 + t) % kFlagSlots;
+        for (int src = 0; src < G; src++) {
+          if (src == rank) continue;
+          const CUdeviceptr fa = (CUdeviceptr)(comm->d_flags + (size_t)src * kFlagSlots + slot);
+          CUresult wr = CUDA_ERROR_NOT_SUPPORTED;
+          if (comm->wait_flush) {
+            wr = comm->fn_wait32((CUstream)st, fa, seq, CU_STREAM_WAIT_VALUE_GEQ | CU_STREAM_WAIT_VALUE_FLUSH);
+            if (wr != CUDA_SUCCESS) comm->wait_flush = false;
+          }
+          if (wr != CUDA_SUCCESS) wr = comm->fn_wait32((CUstream)st, fa, seq, CU_STREAM_WAIT_VALUE_GEQ);
+          if (wr != CUDA_SUCCESS) {
+            drain_exchange();
+            set_error("distributed_inner_join: cuStreamWaitValue32 failed with CUresult %d", (int)wr);
+            return DJ_ERR_CUDA;
+          }
+        }
+        trace.mark(t ? "arrived(R)" : "arrived(L)", st);
+      }
       TableInput in{pc.key, pc.pay, pc.span, pc.d_seg_begin, pc.d_seg_end, nseg, pc.d_seg_parent, sub_bits > 0};
+      trace.mark(t ? "radix(R) begin" : "radix(L) begin", st);
       rc = prepare_side(in, plan, &side[t], arena, st);
       if (rc) return rc;
+      trace.mark(t ? "radix(R) end" : "radix(L) end", st);
     }
     rc = join_prepared(side[swap ? 1 : 0], side[swap ? 0 : 1], plan, out, out_capacity, d_count, swap, st);
     if (rc) return rc;
+    trace.mark("join end", st);
     if (timing) {
       DJ_CUDA_TRY(cudaStreamSynchronize(st));
       double ms = ms_since(tj);
@@ -602,7 +866,11 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   DJ_CUDA_TRY(cudaMemcpyAsync(comm->h_pinned, d_count, 8, cudaMemcpyDeviceToHost, st));
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
   DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
+  if (use_peer)
+    for (int i = 0; i < G; i++)
+      if (i != rank) DJ_CUDA_TRY(cudaStreamSynchronize(comm->peer_stream[i]));  // my buckets may be reused now
   *h_out_count = comm->h_pinned[0];
+  trace.dump(rank);
   // the overflow verdict is collective: every rank returns DJ_ERR_OVERFLOW if any rank's
   // output did not fit, so that callers can retry together
   {

@@ -47,7 +47,23 @@ static std::unique_ptr<table> fused_join(cudf::table_view left, cudf::table_view
   const int64_t nl = left.num_rows(), nr = right.num_rows();
   const int world  = nccl->mpi_size;
   const size_t ws_bytes = dj_distributed_inner_join_workspace_bytes(nl, nr, world, over_decom_factor);
-  rmm::device_buffer ws(ws_bytes);
+  // The library pushes buckets into peers' workspaces through CUDA IPC (copy engines over NVLink),
+  // which needs plain cudaMalloc memory: keep one grow-only workspace per process instead of
+  // taking it from the stream-ordered pool (with pool memory the library falls back to NCCL).
+  static struct Workspace {
+    void* p = nullptr;
+    size_t n = 0;
+    void* data() { return p; }
+    ~Workspace()
+    {
+      if (p) cudaFree(p);
+    }
+  } ws;
+  if (ws.n < ws_bytes) {
+    if (ws.p) CUDA_RT_CALL(cudaFree(ws.p));
+    CUDA_RT_CALL(cudaMalloc(&ws.p, ws_bytes));
+    ws.n = ws_bytes;
+  }
   // first guess for the output: as many rows as the larger input; retried collectively if short
   int64_t capacity = std::max<int64_t>(std::max(nl, nr), 1);
   for (;;) {

@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 TRP="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1"
 F='^\*\|OMP_NUM\|^$\|W09'
 echo "== parity"; timeout 300 $TRP --master-port 29701 tests/test_multi_gpu.py 2>&1 | grep -v "$F" | tail -8
+echo "== timeline"; timeout 300 $TRP --master-port 29709 scripts/trace_timeline.py 2>&1 | grep "trace rank 0"
 echo "== bench"; timeout 400 $TRP --master-port 29702 bench.py --gpus $NP --steps 5 --warmup 3 2>&1 | grep -v "$F" | tail -2 | tee gpurun_out/n${NP}_bench.json | cut -c1-3000
 cd distributed-join_b200
 TR="$TRP --no-python"
