@@ -386,6 +386,14 @@ struct Trace {
   bool on = false;
   cudaEvent_t base = nullptr;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  std::vector<std::pair<const char*, double>> host_marks;  // host wall clock, ms since init
+  std::chrono::high_resolution_clock::time_point t0;
+  void host(const char* name)
+  {
+    if (!on) return;
+    host_marks.push_back({name, std::chrono::duration<double, std::milli>(
+                                  std::chrono::high_resolution_clock::now() - t0).count()});
+  }
   void init(cudaStream_t st)
   {
     const char* e = getenv("DJ_TRACE");
@@ -393,6 +401,7 @@ struct Trace {
     if (!on) return;
     cudaEventCreate(&base);
     cudaEventRecord(base, st);
+    t0 = std::chrono::high_resolution_clock::now();
   }
   void mark(const char* name, cudaStream_t st)
   {
@@ -413,6 +422,7 @@ struct Trace {
       cudaEventDestroy(m.second);
     }
     cudaEventDestroy(base);
+    for (auto& m : host_marks) printf("[trace rank %d] host %8.3f ms  %s\n", rank, m.second, m.first);
     fflush(stdout);
   }
 };
@@ -481,6 +491,17 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   if (rc) return rc;
   Trace trace;
   trace.init(st);
+  // The persistent partition / join kernels leave a couple of SMs idle for the whole call: the
+  // control plane's tiny NCCL all-gathers are kernels too, and a GPU saturated by persistent CTAs
+  // would make each of them wait for a kernel boundary (measured: up to 4 ms per collective).
+  struct ReserveGuard {
+    ReserveGuard()
+    {
+      const char* e = getenv("DJ_SM_RESERVE");
+      set_sm_reserve(e ? atoi(e) : 2);
+    }
+    ~ReserveGuard() { set_sm_reserve(0); }
+  } reserve_guard;
 
   // ---- 0. agree on the join's radix plan from the global table sizes.  When the plan has two
   //         levels, the first one is FUSED into the rank partition on the sender: bucket =
@@ -512,6 +533,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       }
     }
   }
+  trace.host("plan agreed");
   // ---- 0b. copy-engine exchange: map every peer's workspace for this call (cached per allocation)
   bool use_peer = comm->peer_ok && 2 * odf <= kFlagSlots;
   std::vector<char*> peer_ws(world, nullptr);
@@ -545,6 +567,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     for (int r = 0; r < world; r++) ok = ok && oks[r] == 1;
     use_peer = ok;  // identical on every rank; otherwise fall back to the NCCL exchange
   }
+  trace.host("peer workspaces mapped");
   const uint32_t seq = use_peer ? ++comm->seq : 0;
   std::vector<int64_t> peer_piece_off;  // [table][rank][batch][key|pay] byte offsets in the peer's workspace
   peer_piece_off.assign((size_t)2 * world * odf * 2, 0);
@@ -575,17 +598,11 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     PassBuffers pb{};
     pb.in_key = in_key[t]; pb.in_pay[0] = in_pay[t]; pb.out_key = pk[t]; pb.out_pay[0] = pp[t];
     pb.nrows = n_in[t]; pb.d_child_off = d_off[t]; pb.d_child_cnt = d_cnt[t];
-    // the right table is partitioned while the left one is already on the wire: leave a few
-    // SMs to NCCL's copy kernels (DJ_SM_RESERVE, default 0 = let the hardware interleave)
-    if (t == 1) {
-      const char* e = getenv("DJ_SM_RESERVE");
-      set_sm_reserve(e ? atoi(e) : 0);
-    }
     rc = run_partition_pass(desc, pb, pws, pw, st);
-    set_sm_reserve(0);
     if (rc) return rc;
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_part[t], st));
     trace.mark(t ? "partition(R) done" : "partition(L) done", st);
+    trace.host(t ? "partition(R) launched" : "partition(L) launched");
   }
 
   // ---- 2-4. table by table: sizes (communicate_sizes, on the control communicator), receive
@@ -723,9 +740,11 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
       tcomm = std::chrono::high_resolution_clock::now();
     }
+    trace.host(t ? "offsets(R) on host" : "offsets(L) on host");
     allc[t].resize((size_t)world * nbk);
     rc = ctrl_allgather(comm, cntv[t].data(), nbk, allc[t].data());
     if (rc) return rc;
+    trace.host(t ? "counts(R) gathered" : "counts(L) gathered");
 
     // receive layout: per (batch) one padded piece per source, holding that source's F1s
     // sub-buckets back to back
@@ -746,9 +765,10 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       max_span[t] = std::max(max_span[t], pc.span);
     }
     if (t == 1) need += side_ws_bytes(max_span[0], plan, nseg) + side_ws_bytes(max_span[1], plan, nseg) + 4096;
-    rc = agree_fits(need);
-    if (rc) return rc;
-    for (int b = 0; b < odf; b++) {
+    // pieces are laid out first (pure arithmetic), then ONE collective carries both the
+    // "it fits" verdict and the piece offsets the peers need for their pushes
+    const bool fits = need <= workspace_bytes;
+    for (int b = 0; b < odf && fits; b++) {
       const size_t i  = (size_t)b * 2 + t;
       Piece& pc       = pieces[i];
       pc.key          = arena.take<int64_t>((size_t)pc.span + 8);
@@ -756,11 +776,35 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       pc.d_seg_begin  = arena.take<int64_t>((size_t)nseg);
       pc.d_seg_end    = arena.take<int64_t>((size_t)nseg);
       pc.d_seg_parent = arena.take<int>((size_t)nseg);
-      if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) {
-        drain_exchange();
-        set_error("distributed_inner_join: workspace too small for receive buffers");
-        return DJ_ERR_WORKSPACE;
+    }
+    {
+      std::vector<int64_t> mine_off((size_t)odf * 2 + 1), all_off((size_t)world * (odf * 2 + 1));
+      bool ok_local = fits;
+      for (int b = 0; b < odf && fits; b++) {
+        Piece& pc = pieces[(size_t)b * 2 + t];
+        if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) ok_local = false;
       }
+      mine_off[0] = ok_local ? 1 : 0;
+      for (int b = 0; b < odf && ok_local; b++) {
+        mine_off[1 + (size_t)b * 2]     = (char*)pieces[(size_t)b * 2 + t].key - (char*)d_workspace;
+        mine_off[1 + (size_t)b * 2 + 1] = (char*)pieces[(size_t)b * 2 + t].pay - (char*)d_workspace;
+      }
+      rc = ctrl_allgather(comm, mine_off.data(), odf * 2 + 1, all_off.data());
+      if (rc) return rc;
+      for (int r = 0; r < world; r++) {
+        if (!all_off[(size_t)r * (odf * 2 + 1)]) {
+          drain_exchange();
+          set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
+                    "(this rank needs %zu of %zu bytes)", r, need, workspace_bytes);
+          return DJ_ERR_WORKSPACE;
+        }
+        for (int k = 0; k < odf * 2; k++)
+          peer_piece_off[((size_t)t * world + r) * odf * 2 + k] = all_off[(size_t)r * (odf * 2 + 1) + 1 + k];
+      }
+    }
+    for (int b = 0; b < odf; b++) {
+      const size_t i = (size_t)b * 2 + t;
+      Piece& pc      = pieces[i];
       int64_t* hb = hseg + i * 3 * nseg;
       int* hpar   = reinterpret_cast<int*>(hb + 2 * (size_t)nseg);
       for (int s = 0; s < G; s++) {
@@ -778,21 +822,10 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_parent, hpar, (size_t)nseg * 4, cudaMemcpyHostToDevice, comm->ctrl_stream));
     }
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_seg[t], comm->ctrl_stream));
-    if (use_peer) {
-      std::vector<int64_t> mine_off((size_t)odf * 2), all_off((size_t)world * odf * 2);
-      for (int b = 0; b < odf; b++) {
-        mine_off[(size_t)b * 2]     = (char*)pieces[(size_t)b * 2 + t].key - (char*)d_workspace;
-        mine_off[(size_t)b * 2 + 1] = (char*)pieces[(size_t)b * 2 + t].pay - (char*)d_workspace;
-      }
-      rc = ctrl_allgather(comm, mine_off.data(), odf * 2, all_off.data());
-      if (rc) return rc;
-      for (int r = 0; r < world; r++)
-        for (int k = 0; k < odf * 2; k++)
-          peer_piece_off[((size_t)t * world + r) * odf * 2 + k] = all_off[(size_t)r * odf * 2 + k];
-    }
 
     // exchanges in batch order (b,L),(b,R); what can start now: (0,L) after the left table's
     // sizes, everything else once the right table's sizes are known
+    trace.host(t ? "pieces(R) laid out" : "pieces(L) laid out");
     DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_part[t], 0));
     if (t == 0) {
       rc = issue_exchange(0, 0);
@@ -813,6 +846,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     for (int b = 0; b < odf; b++)
       printf("Rank %d: All-to-all communication on batch %d takes %.0fms\n", rank, b, opts->t_comm_ms / odf);
   }
+  trace.host("exchanges issued");
   DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_seg[0], 0));
   DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_seg[1], 0));
 
@@ -863,9 +897,11 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       printf("Rank %d: Local join on batch %d takes %.0fms\n", rank, b, ms);
     }
   }
+  trace.host("join launched");
   DJ_CUDA_TRY(cudaMemcpyAsync(comm->h_pinned, d_count, 8, cudaMemcpyDeviceToHost, st));
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
   DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
+  trace.host("streams drained");
   if (use_peer)
     for (int i = 0; i < G; i++)
       if (i != rank) DJ_CUDA_TRY(cudaStreamSynchronize(comm->peer_stream[i]));  // my buckets may be reused now
