@@ -511,6 +511,15 @@ ORACLE_API int64_t oracle_partitioned_join_omp(const int64_t* bk, const int64_t*
   return total;
 }
 
+ORACLE_API void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 ORACLE_API int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         L.oracle_partitioned_join_omp.argtypes = [i64p, i64p, C.c_int64, i64p, i64p, C.c_int64, C.c_int, C.c_uint32,
                                                   C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_threads.restype = None
+        L.oracle_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -197,6 +199,10 @@ def partitioned_join_omp(bk, bp, pk, pp, nparts=1024, seed=SEED_NVLINK, checksum
                                           C.byref(sec), ck if checksum else None, C.byref(thr))
     return {"n_out": int(n), "seconds": sec.value, "threads": thr.value,
             "checksum": (int(ck[0]), int(ck[1])) if checksum else None}
+
+
+def set_threads(n: int) -> None:
+    lib().oracle_set_threads(int(n))
 
 
 def num_threads() -> int:
