@@ -711,22 +711,6 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       for (int i = 0; i < G; i++)
         if (i != rank) cudaStreamSynchronize(comm->peer_stream[i]);
   };
-  // collective verdict on the control communicator; drains the bulk stream before failing
-  auto agree_fits = [&](size_t need) -> int {
-    int64_t ok = need <= workspace_bytes ? 1 : 0;
-    std::vector<int64_t> oks(world);
-    int r2 = ctrl_allgather(comm, &ok, 1, oks.data());
-    if (r2) return r2;
-    for (int r = 0; r < world; r++)
-      if (!oks[r]) {
-        drain_exchange();
-        set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
-                  "(this rank needs %zu of %zu bytes)", r, need, workspace_bytes);
-        return DJ_ERR_WORKSPACE;
-      }
-    return DJ_OK;
-  };
-
   for (int t = 0; t < 2; t++) {
     // sizes of table t: wait only for ITS partition pass
     DJ_CUDA_TRY(cudaStreamWaitEvent(comm->ctrl_stream, comm->ev_part[t], 0));
