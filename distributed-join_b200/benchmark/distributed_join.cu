@@ -90,8 +90,6 @@ int main(int argc, char* argv[])
   set_cuda_device();
   parse_command_line_arguments(argc, argv);
   report_configuration();
-  if (key_type != "int64_t" || payload_type != "int64_t")
-    throw std::runtime_error("the B200 build benchmarks int64_t keys and payloads");
   if (std::max(BUILD_TABLE_NROWS_EACH_RANK, PROBE_TABLE_NROWS_EACH_RANK) > INT32_MAX)
     throw std::runtime_error("per-rank tables are limited to cudf::size_type rows at this API level");
 
@@ -109,9 +107,22 @@ int main(int argc, char* argv[])
   if (COMPRESSION) warmup_nvcomp();
 
   std::unique_ptr<cudf::table> left, right;
-  std::tie(left, right) = generate_tables_distributed<int64_t, int64_t>(
-    (cudf::size_type)BUILD_TABLE_NROWS_EACH_RANK, (cudf::size_type)PROBE_TABLE_NROWS_EACH_RANK, SELECTIVITY,
-    RAND_MAX_VAL, IS_BUILD_TABLE_KEY_UNIQUE, communicator);
+  auto generate = [&](auto key_tag, auto payload_tag) {
+    using KEY_T     = decltype(key_tag);
+    using PAYLOAD_T = decltype(payload_tag);
+    std::tie(left, right) = generate_tables_distributed<KEY_T, PAYLOAD_T>(
+      (cudf::size_type)BUILD_TABLE_NROWS_EACH_RANK, (cudf::size_type)PROBE_TABLE_NROWS_EACH_RANK, SELECTIVITY,
+      (KEY_T)RAND_MAX_VAL, IS_BUILD_TABLE_KEY_UNIQUE, communicator);
+  };
+  // same type matrix as the reference driver (benchmark/distributed_join.cu:225-253); 4-byte columns
+  // are widened to the kernels' 8-byte rows inside the library shim
+  if (key_type == "int64_t" && payload_type == "int64_t") generate(int64_t{}, int64_t{});
+  else if (key_type == "int64_t" && payload_type == "int32_t") generate(int64_t{}, int32_t{});
+  else if (key_type == "int32_t" && payload_type == "int64_t") generate(int32_t{}, int64_t{});
+  else if (key_type == "int32_t" && payload_type == "int32_t") generate(int32_t{}, int32_t{});
+  else throw std::runtime_error("Unknown key / payload type");
+  if (key_type == "int32_t" && RAND_MAX_VAL * (int64_t)mpi_size > INT32_MAX)
+    throw std::runtime_error("int32_t keys: rand_max * ranks exceeds the key range");
 
   auto left_compression_options  = generate_compression_options_distributed(left->view(), COMPRESSION);
   auto right_compression_options = generate_compression_options_distributed(right->view(), COMPRESSION);

@@ -1,15 +1,73 @@
 #include "cudf_shim.hpp"
 
+#include <algorithm>
+#include <string>
+
 namespace cudf {
 
 namespace {
-void require_i64(table_view const& t, const char* what)
+void require_fixed_width(table_view const& t, const char* what)
 {
   for (auto const& c : t)
-    if (c.type().id() != type_id::INT64)
-      throw std::runtime_error(std::string(what) + ": the B200 build handles INT64 columns (other widths: see DESIGN.md)");
+    if (!is_fixed_width(c.type()))
+      throw std::runtime_error(std::string(what) + ": the B200 build handles fixed-width columns only");
 }
+
+__global__ void widen_kernel(const int32_t* in, int64_t* out, int64_t n)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+__global__ void narrow_kernel(const int64_t* in, int32_t* out, int64_t n)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int32_t)in[i];
+}
+int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 16)); }
 }  // namespace
+
+bool all_i64(table_view const& t)
+{
+  for (auto const& c : t)
+    if (size_of(c.type()) != 8) return false;
+  return true;
+}
+
+std::unique_ptr<table> widen_to_i64(table_view const& t)
+{
+  require_fixed_width(t, "widen");
+  std::vector<std::unique_ptr<column>> cols;
+  const int64_t n = t.num_rows();
+  for (auto const& c : t) {
+    cols.push_back(make_fixed_width_column(data_type(type_id::INT64), (size_type)n));
+    if (n == 0) continue;
+    if (size_of(c.type()) == 8)
+      CUDA_RT_CALL(cudaMemcpyAsync(cols.back()->mutable_view().head(), c.head(), (size_t)n * 8,
+                                   cudaMemcpyDeviceToDevice, nullptr));
+    else
+      widen_kernel<<<grid_for(n), 256>>>(c.head<int32_t>(), cols.back()->mutable_view().head<int64_t>(), n);
+  }
+  CUDA_RT_CALL(cudaGetLastError());
+  return std::make_unique<table>(std::move(cols));
+}
+
+std::unique_ptr<table> narrow_like(table_view const& t, std::vector<data_type> const& types)
+{
+  if ((size_t)t.num_columns() != types.size()) throw std::runtime_error("narrow_like: column count mismatch");
+  std::vector<std::unique_ptr<column>> cols;
+  const int64_t n = t.num_rows();
+  for (size_type c = 0; c < t.num_columns(); c++) {
+    cols.push_back(make_fixed_width_column(types[c], (size_type)n));
+    if (n == 0) continue;
+    if (size_of(types[c]) == 8)
+      CUDA_RT_CALL(cudaMemcpyAsync(cols.back()->mutable_view().head(), t.column(c).head(), (size_t)n * 8,
+                                   cudaMemcpyDeviceToDevice, nullptr));
+    else
+      narrow_kernel<<<grid_for(n), 256>>>(t.column(c).head<int64_t>(), cols.back()->mutable_view().head<int32_t>(), n);
+  }
+  CUDA_RT_CALL(cudaGetLastError());
+  return std::make_unique<table>(std::move(cols));
+}
 
 std::pair<std::unique_ptr<table>, std::vector<size_type>> hash_partition(
   table_view const& input, std::vector<size_type> const& columns_to_hash, int num_partitions, hash_id hash_function,
@@ -18,7 +76,14 @@ std::pair<std::unique_ptr<table>, std::vector<size_type>> hash_partition(
   if (columns_to_hash.size() != 1) throw std::runtime_error("hash_partition: exactly one key column is supported");
   if (input.num_columns() < 2 || input.num_columns() > 4)
     throw std::runtime_error("hash_partition: 2..4 columns (key + 1..3 payload columns) are supported");
-  require_i64(input, "hash_partition");
+  require_fixed_width(input, "hash_partition");
+  if (!all_i64(input)) {
+    std::vector<data_type> types;
+    for (auto const& c : input) types.push_back(c.type());
+    auto wide   = widen_to_i64(input);
+    auto result = hash_partition(wide->view(), columns_to_hash, num_partitions, hash_function, seed);
+    return {narrow_like(result.first->view(), types), std::move(result.second)};
+  }
   const size_type n   = input.num_rows();
   const size_type key = columns_to_hash[0];
 
@@ -52,8 +117,16 @@ std::unique_ptr<table> inner_join(table_view const& left, table_view const& righ
 {
   if (left_on.size() != 1 || right_on.size() != 1 || left.num_columns() != 2 || right.num_columns() != 2)
     throw std::runtime_error("inner_join: one key column and one payload column per side are supported");
-  require_i64(left, "inner_join");
-  require_i64(right, "inner_join");
+  require_fixed_width(left, "inner_join");
+  require_fixed_width(right, "inner_join");
+  if (!all_i64(left) || !all_i64(right)) {
+    std::vector<data_type> types;
+    for (auto const& c : left) types.push_back(c.type());
+    for (auto const& c : right) types.push_back(c.type());
+    auto wl = widen_to_i64(left), wr = widen_to_i64(right);
+    auto joined = inner_join(wl->view(), wr->view(), left_on, right_on);
+    return narrow_like(joined->view(), types);
+  }
   const size_type lk = left_on[0], rk = right_on[0];
   const int64_t nl = left.num_rows(), nr = right.num_rows();
   // build on the smaller side; the output stays left columns ++ right columns

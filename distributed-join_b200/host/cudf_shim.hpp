@@ -125,7 +125,20 @@ namespace cudf {
 
 using size_type = int32_t;  // as in cuDF 0.19; the C ABI underneath counts rows in int64
 
-enum class type_id : int32_t { EMPTY = 0, INT32, INT64, STRING };
+// fixed-width types of the reference's test matrix (test/compare_against_single_gpu.cu:237-268):
+// 4-byte and 8-byte integers plus the timestamp / duration types that are integers underneath
+enum class type_id : int32_t {
+  EMPTY = 0,
+  INT32,
+  INT64,
+  TIMESTAMP_DAYS,          // int32
+  TIMESTAMP_MILLISECONDS,  // int64
+  TIMESTAMP_NANOSECONDS,   // int64
+  DURATION_DAYS,           // int32
+  DURATION_SECONDS,        // int64
+  DURATION_MICROSECONDS,   // int64
+  STRING
+};
 enum class hash_id : int32_t { HASH_IDENTITY = DJ_HASH_IDENTITY, HASH_MURMUR3 = DJ_HASH_MURMUR3 };
 constexpr uint32_t DEFAULT_HASH_SEED = 0;
 
@@ -150,12 +163,18 @@ constexpr type_id type_to_id<int64_t>() { return type_id::INT64; }
 inline std::size_t size_of(data_type t)
 {
   switch (t.id()) {
-    case type_id::INT32: return 4;
-    case type_id::INT64: return 8;
+    case type_id::INT32:
+    case type_id::TIMESTAMP_DAYS:
+    case type_id::DURATION_DAYS: return 4;
+    case type_id::INT64:
+    case type_id::TIMESTAMP_MILLISECONDS:
+    case type_id::TIMESTAMP_NANOSECONDS:
+    case type_id::DURATION_SECONDS:
+    case type_id::DURATION_MICROSECONDS: return 8;
     default: throw std::runtime_error("cudf shim: size_of is defined for fixed-width types only");
   }
 }
-inline bool is_fixed_width(data_type t) { return t.id() == type_id::INT32 || t.id() == type_id::INT64; }
+inline bool is_fixed_width(data_type t) { return t.id() != type_id::EMPTY && t.id() != type_id::STRING; }
 
 class column_view {
  public:
@@ -253,15 +272,22 @@ inline std::unique_ptr<column> make_numeric_column(data_type t, size_type n, cud
   return make_fixed_width_column(t, n, stream);
 }
 
+// The kernels underneath move 8-byte values.  4-byte columns are widened (sign-extended) into
+// temporary INT64 columns on the way in and narrowed back on the way out; results are identical,
+// only the partition a key lands in differs from cuDF's 4-byte murmur (results never depend on it).
+std::unique_ptr<table> widen_to_i64(table_view const& t);                     // every column -> INT64
+std::unique_ptr<table> narrow_like(table_view const& t, std::vector<data_type> const& types);
+bool all_i64(table_view const& t);
+
 // cudf::hash_partition(table, {key column}, nparts, hash, seed) -> (partitioned table, offsets[nparts])
-// (call sites src/distributed_join.cpp:213-225, src/shuffle_on.cpp:59-60).  INT64 columns, one
+// (call sites src/distributed_join.cpp:213-225, src/shuffle_on.cpp:59-60).  Fixed-width columns, one
 // key column, up to three further columns; runs dj_hash_partition_i64 on stream 0.
 std::pair<std::unique_ptr<table>, std::vector<size_type>> hash_partition(
   table_view const& input, std::vector<size_type> const& columns_to_hash, int num_partitions,
   hash_id hash_function = hash_id::HASH_MURMUR3, uint32_t seed = DEFAULT_HASH_SEED);
 
 // cudf::inner_join(left, right, {0}, {0}) -> left columns ++ right columns
-// (src/distributed_join.cpp:79).  Two INT64 columns per side; runs dj_inner_join_i64.
+// (src/distributed_join.cpp:79).  Two fixed-width columns per side; runs dj_inner_join_i64.
 std::unique_ptr<table> inner_join(table_view const& left, table_view const& right,
                                   std::vector<size_type> const& left_on,
                                   std::vector<size_type> const& right_on);

@@ -24,10 +24,10 @@ static int get_nvl_partition_size(int mpi_size, int nvlink_domain_size)
   return 1;
 }
 
-static bool is_key_payload_i64(cudf::table_view t, vector<cudf::size_type> const& on)
+static bool is_key_payload(cudf::table_view t, vector<cudf::size_type> const& on)
 {
-  return t.num_columns() == 2 && on.size() == 1 && on[0] == 0 &&
-         t.column(0).type().id() == cudf::type_id::INT64 && t.column(1).type().id() == cudf::type_id::INT64;
+  return t.num_columns() == 2 && on.size() == 1 && on[0] == 0 && cudf::is_fixed_width(t.column(0).type()) &&
+         cudf::is_fixed_width(t.column(1).type());
 }
 
 static std::unique_ptr<table> local_join_helper(cudf::table_view left, cudf::table_view right,
@@ -111,9 +111,19 @@ std::unique_ptr<table> distributed_inner_join(cudf::table_view left, cudf::table
 
   // ---- fast path: one NVLink domain covering all ranks, int64 key + int64 payload
   auto* nccl = dynamic_cast<NCCLCommunicator*>(communicator);
-  if (nccl && group == mpi_size && is_key_payload_i64(left, left_on) && is_key_payload_i64(right, right_on)) {
+  if (nccl && group == mpi_size && is_key_payload(left, left_on) && is_key_payload(right, right_on)) {
+    if (cudf::all_i64(left) && cudf::all_i64(right)) {
+      CUDA_RT_CALL(cudaStreamSynchronize(nullptr));
+      return fused_join(left, right, nccl, over_decom_factor, report_timing);
+    }
+    // 4-byte columns: widen into temporary INT64 tables, join, narrow back to the callers' types
+    std::vector<cudf::data_type> types;
+    for (auto const& c : left) types.push_back(c.type());
+    for (auto const& c : right) types.push_back(c.type());
+    auto wl = cudf::widen_to_i64(left), wr = cudf::widen_to_i64(right);
     CUDA_RT_CALL(cudaStreamSynchronize(nullptr));
-    return fused_join(left, right, nccl, over_decom_factor, report_timing);
+    auto joined = fused_join(wl->view(), wr->view(), nccl, over_decom_factor, report_timing);
+    return cudf::narrow_like(joined->view(), types);
   }
 
   // ---- general path, stage by stage like src/distributed_join.cpp:152-339

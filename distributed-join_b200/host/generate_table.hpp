@@ -64,8 +64,9 @@ std::pair<std::unique_ptr<cudf::table>, std::unique_ptr<cudf::table>> generate_t
   cudf::size_type build_table_nrows_per_rank, cudf::size_type probe_table_nrows_per_rank, double selectivity,
   KEY_T rand_max_per_rank, bool uniq_build_tbl_keys, Communicator* communicator)
 {
-  static_assert(std::is_same<KEY_T, int64_t>::value && std::is_same<PAYLOAD_T, int64_t>::value,
-                "the B200 build generates int64 keys and payloads");
+  static_assert((std::is_same<KEY_T, int64_t>::value || std::is_same<KEY_T, int32_t>::value) &&
+                  (std::is_same<PAYLOAD_T, int64_t>::value || std::is_same<PAYLOAD_T, int32_t>::value),
+                "keys and payloads are int32_t or int64_t");
   const int world = communicator->mpi_size, rank = communicator->mpi_rank;
   const int64_t bchunk = build_table_nrows_per_rank / world, pchunk = probe_table_nrows_per_rank / world;
   dj_gen_params g{};
@@ -91,5 +92,13 @@ std::pair<std::unique_ptr<cudf::table>, std::unique_ptr<cudf::table>> generate_t
                                  pv.column(1).head<int64_t>() + src * pchunk, nullptr));
   }
   CUDA_RT_CALL(cudaStreamSynchronize(nullptr));
+  if (!std::is_same<KEY_T, int64_t>::value || !std::is_same<PAYLOAD_T, int64_t>::value) {
+    // generated as int64, handed out in the requested widths (values fit: rand_max is a size_type)
+    std::vector<cudf::data_type> types{cudf::data_type(cudf::type_to_id<KEY_T>()),
+                                       cudf::data_type(cudf::type_to_id<PAYLOAD_T>())};
+    build = cudf::narrow_like(build->view(), types);
+    probe = cudf::narrow_like(probe->view(), types);
+    CUDA_RT_CALL(cudaStreamSynchronize(nullptr));
+  }
   return {std::move(build), std::move(probe)};
 }

@@ -16,15 +16,17 @@
 #include "../host/error.hpp"
 #include "../host/setup.hpp"
 
-__global__ void fill_multiples(int64_t* key, int64_t* payload, int64_t first_row, int64_t n, int64_t multiple)
+template <typename T>
+__global__ void fill_multiples(T* key, T* payload, int64_t first_row, int64_t n, int64_t multiple)
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    key[i]     = (first_row + i) * multiple;
-    payload[i] = first_row + i;
+    key[i]     = (T)((first_row + i) * multiple);
+    payload[i] = (T)(first_row + i);
   }
 }
 
-__global__ void count_violations(const int64_t* c0, const int64_t* c1, const int64_t* c2, const int64_t* c3,
+template <typename T>
+__global__ void count_violations(const T* c0, const T* c1, const T* c2, const T* c3,
                                  int64_t n, unsigned long long* bad)
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -33,23 +35,25 @@ __global__ void count_violations(const int64_t* c0, const int64_t* c1, const int
   }
 }
 
+template <typename T>
 static std::unique_ptr<cudf::table> slice_of_multiples(int64_t size, int64_t multiple, int rank, int world)
 {
   const int64_t lo = size * rank / world, hi = size * (rank + 1) / world;
   std::vector<std::unique_ptr<cudf::column>> cols;
   for (int c = 0; c < 2; c++)
-    cols.push_back(cudf::make_numeric_column(cudf::data_type(cudf::type_id::INT64), (cudf::size_type)(hi - lo)));
-  fill_multiples<<<256, 256>>>(cols[0]->mutable_view().head<int64_t>(), cols[1]->mutable_view().head<int64_t>(), lo,
-                               hi - lo, multiple);
+    cols.push_back(cudf::make_numeric_column(cudf::data_type(cudf::type_to_id<T>()), (cudf::size_type)(hi - lo)));
+  fill_multiples<T><<<256, 256>>>(cols[0]->mutable_view().template head<T>(), cols[1]->mutable_view().template head<T>(), lo,
+                                  hi - lo, multiple);
   CUDA_RT_CALL(cudaDeviceSynchronize());
   return std::make_unique<cudf::table>(std::move(cols));
 }
 
+template <typename T>
 static bool run_test(int64_t size, int odf, int nvl, Communicator* communicator)
 {
   const int rank = communicator->mpi_rank, world = communicator->mpi_size;
-  auto left  = slice_of_multiples(size, 3, rank, world);
-  auto right = slice_of_multiples(size, 5, rank, world);
+  auto left  = slice_of_multiples<T>(size, 3, rank, world);
+  auto right = slice_of_multiples<T>(size, 5, rank, world);
   auto result = distributed_inner_join(left->view(), right->view(), {0}, {0}, communicator,
                                        generate_none_compression_options(left->view()),
                                        generate_none_compression_options(right->view()), odf, false, nullptr, nvl);
@@ -59,8 +63,9 @@ static bool run_test(int64_t size, int odf, int nvl, Communicator* communicator)
   if (result->num_rows() > 0) {
     if (result->num_columns() != 4) return false;
     auto v = result->view();
-    count_violations<<<256, 256>>>(v.column(0).head<int64_t>(), v.column(1).head<int64_t>(),
-                                   v.column(2).head<int64_t>(), v.column(3).head<int64_t>(), v.num_rows(), d_bad);
+    if (!(v.column(0).type() == cudf::data_type(cudf::type_to_id<T>()))) return false;  // types survive the join
+    count_violations<T><<<256, 256>>>(v.column(0).template head<T>(), v.column(1).template head<T>(), v.column(2).template head<T>(),
+                                      v.column(3).template head<T>(), v.num_rows(), d_bad);
   }
   unsigned long long bad = 0;
   CUDA_RT_CALL(cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost));
@@ -69,7 +74,7 @@ static bool run_test(int64_t size, int odf, int nvl, Communicator* communicator)
   const int64_t total_bad  = dj_bootstrap::allreduce_sum((int64_t)bad);
   const bool ok            = total_rows == size / 5 && total_bad == 0;
   if (rank == 0)
-    std::cerr << "size " << size << " odf " << odf << " nvl " << nvl << ": rows " << total_rows << " (expected "
+    std::cerr << (sizeof(T) == 4 ? "int32 " : "int64 ") << "size " << size << " odf " << odf << " nvl " << nvl << ": rows " << total_rows << " (expected "
               << size / 5 << "), violations " << total_bad << (ok ? " -> passes successfully" : " -> FAILED")
               << std::endl;
   return ok;
@@ -87,12 +92,15 @@ int main(int argc, char* argv[])
   bool ok = true;
   // the reference's case list (test/compare_against_analytical.cu:194-201) without compression;
   // nvl = world exercises the fused NVLink path, nvl 1 / 2 the staged general path
-  ok &= run_test(30'000, 1, 1, communicator);
-  ok &= run_test(300'000, 1, 1, communicator);
-  ok &= run_test(300'000, 4, 1, communicator);
-  ok &= run_test(3'000'000, 1, world, communicator);
-  ok &= run_test(3'000'000, 4, world, communicator);
-  ok &= run_test(3'000'000, 4, 2, communicator);
+  // the reference generates int32 tables here (test/compare_against_analytical.cu:64-81)
+  ok &= run_test<int32_t>(30'000, 1, 1, communicator);
+  ok &= run_test<int32_t>(300'000, 4, world, communicator);
+  ok &= run_test<int64_t>(30'000, 1, 1, communicator);
+  ok &= run_test<int64_t>(300'000, 1, 1, communicator);
+  ok &= run_test<int64_t>(300'000, 4, 1, communicator);
+  ok &= run_test<int64_t>(3'000'000, 1, world, communicator);
+  ok &= run_test<int64_t>(3'000'000, 4, world, communicator);
+  ok &= run_test<int64_t>(3'000'000, 4, 2, communicator);
   destroy_memory_pool_and_communicator(communicator, registered_mr, pool_mr, "NCCL", "none");
   dj_bootstrap::finalize();
   if (!ok) return 1;
