@@ -877,10 +877,14 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   dev.shift      = desc.shift;
   dev.pow2       = desc.mode == 2 ? (desc.nparts & (desc.nparts - 1)) == 0 : (desc.F & (desc.F - 1)) == 0;
   dev.nparts     = desc.nparts;
+#ifdef DJ_EXPERIMENTS  // measurement aid only (wrong results): contiguous write-out, see DESIGN.md 7.1
   {
     const char* e    = getenv("DJ_SCATTER_DEBUG_LINEAR");
     dev.debug_linear = e && e[0] == '1';
   }
+#else
+  dev.debug_linear = 0;
+#endif
   dev.sub_bits   = desc.sub_bits;
 
   const int hist_grid = sm_count() * 4;
