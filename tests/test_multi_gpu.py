@@ -57,6 +57,52 @@ def main():
             print(f"case nb={nb} np={np_} sel={sel} unique={unique} odf={odf}: rows {n_total} vs oracle {n_ref} "
                   f"-> {'OK' if ok else 'MISMATCH'}", flush=True)
             failures += 0 if ok else 1
+    # ---- edge cases with explicit, rank-dependent tables: an empty slice on one rank, tiny tables,
+    #      uneven slices, heavy duplicates (the generator always deals equal slices)
+    def explicit_case(name, make):
+        nonlocal failures
+        lk, lp, rk, rp = [np.ascontiguousarray(a, dtype=np.int64) for a in make(rank, world)]
+        t = lambda a: torch.from_numpy(a).to(dev)
+        res = dj.distributed_inner_join(comm, t(lk), t(lp), t(rk), t(rp), odf=2 if "odf2" in name else 1)
+        ck = dj.multiset_checksum4(*res.cols) if res.n_out else (0, 0)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (lk, lp, rk, rp, res.n_out, ck))
+        if rank == 0:
+            gl = [np.concatenate([g[i] for g in gathered]) for i in range(4)]
+            n_ref, ref = O.inner_join(*gl)
+            n_total = sum(g[4] for g in gathered)
+            c0 = sum(g[5][0] for g in gathered) & 0xFFFFFFFFFFFFFFFF
+            c1 = sum(g[5][1] for g in gathered) & 0xFFFFFFFFFFFFFFFF
+            ok = n_total == n_ref and (n_ref == 0 or (c0, c1) == O.multiset_checksum4(*ref))
+            print(f"case {name}: rows {n_total} vs oracle {n_ref} -> {'OK' if ok else 'MISMATCH'}", flush=True)
+            failures += 0 if ok else 1
+
+    def empty_on_rank0(r, w):
+        nl = 0 if r == 0 else 1000
+        lk = np.arange(nl) * 3 + r
+        rk = np.arange(500) * 2 + r
+        return lk, np.arange(nl) + 10 * r, rk, np.arange(500) + 7 * r
+
+    def tiny_with_duplicates(r, w):
+        lk = np.array([1, 1, 2, 3, 5, 8, 13, 21, 34, 55]) + (r % 2)
+        rk = np.array([1, 2, 2, 3, 3, 3, 5, 8, 8, 89])
+        return lk, np.arange(10) + 100 * r, rk, np.arange(10) + 1000 * r
+
+    def uneven_slices(r, w):
+        rng = np.random.default_rng(100 + r)
+        nl, nr = (r + 1) * 100_000, (w - r) * 150_000
+        return (rng.integers(0, 400_000, nl), np.arange(nl) + r * 10**7, rng.integers(0, 400_000, nr),
+                np.arange(nr) + r * 10**8)
+
+    def everything_empty_right(r, w):
+        return np.arange(1000) + r, np.arange(1000), np.empty(0, np.int64), np.empty(0, np.int64)
+
+    explicit_case("empty left slice on rank 0", empty_on_rank0)
+    explicit_case("tiny tables with duplicates", tiny_with_duplicates)
+    explicit_case("uneven slices, duplicates on both sides", uneven_slices)
+    explicit_case("uneven slices odf2", uneven_slices)
+    explicit_case("globally empty right table", everything_empty_right)
+
     comm.destroy()
     f = torch.tensor([failures], device=dev)
     dist.broadcast(f, 0)
