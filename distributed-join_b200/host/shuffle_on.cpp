@@ -1,50 +1,29 @@
 #include "shuffle_on.hpp"
 
-#include <iostream>
-
-#include "bootstrap.hpp"
 #include "error.hpp"
+#include "stage_timer.hpp"
 
-std::unique_ptr<cudf::table> shuffle_on(cudf::table_view const& input,
-                                        std::vector<cudf::size_type> const& on_columns,
-                                        CommunicationGroup comm_group, Communicator* communicator,
-                                        std::vector<ColumnCompressionOptions> compression_options,
-                                        cudf::hash_id hash_function, uint32_t hash_seed, bool report_timing,
-                                        void* preallocated_pinned_buffer)
+std::unique_ptr<cudf::table> shuffle_on(
+  cudf::table_view const& input, std::vector<cudf::size_type> const& on_columns, CommunicationGroup comm_group,
+  Communicator* communicator, std::vector<ColumnCompressionOptions> compression_options,
+  cudf::hash_id hash_function, uint32_t hash_seed, bool report_timing, void* preallocated_pinned_buffer)
 {
-  const int rank = communicator->mpi_rank;
-  double t0      = report_timing ? dj_bootstrap::wtime() : 0.0;
+  StageTimer timer(report_timing, communicator->mpi_rank);
 
-  // stage 1: one bucket per group member (libdj_b200 radix hash-partition kernel)
+  // stage 1: libdj_b200's radix hash-partition kernel, one bucket per group member.  cuDF hands
+  // back the bucket start offsets only; the exchange wants the closing offset as well.
   auto partitioned = cudf::hash_partition(input, on_columns, comm_group.size(), hash_function, hash_seed);
   CUDA_RT_CALL(cudaStreamSynchronize(nullptr));
+  std::unique_ptr<cudf::table>& buckets  = partitioned.first;
   std::vector<cudf::size_type>& offsets = partitioned.second;
-  offsets.push_back(partitioned.first->num_rows());
-  if (report_timing) {
-    std::cout << "Rank " << rank << ": Hash partition in shuffle takes " << (dj_bootstrap::wtime() - t0) * 1e3
-              << "ms" << std::endl;
-    t0 = dj_bootstrap::wtime();
-  }
+  offsets.push_back(buckets->num_rows());
+  timer.lap("Hash partition in shuffle");
 
-  // stage 2: exchange (own bucket by device copy, the rest over NVLink)
-  AllToAllCommunicator exchange(partitioned.first->view(), offsets, comm_group, communicator,
-                                std::move(compression_options), true);
-  std::unique_ptr<cudf::table> shuffled = exchange.allocate_communicated_table();
-  exchange.launch_communication(shuffled->mutable_view(), report_timing, preallocated_pinned_buffer);
-  if (report_timing)
-    std::cout << "Rank " << rank << ": All-to-all communication in shuffle takes "
-              << (dj_bootstrap::wtime() - t0) * 1e3 << "ms" << std::endl;
-  return shuffled;
-}
-
-std::unique_ptr<cudf::table> shuffle_on(cudf::table_view const& input,
-                                        std::vector<cudf::size_type> const& on_columns,
-                                        Communicator* communicator,
-                                        std::vector<ColumnCompressionOptions> compression_options,
-                                        cudf::hash_id hash_function, uint32_t hash_seed, bool report_timing,
-                                        void* preallocated_pinned_buffer)
-{
-  return shuffle_on(input, on_columns, CommunicationGroup(communicator->mpi_size, 1), communicator,
-                    std::move(compression_options), hash_function, hash_seed, report_timing,
-                    preallocated_pinned_buffer);
+  // stage 2: own bucket by device copy, every other bucket over NVLink, straight into the result
+  AllToAllCommunicator exchange(buckets->view(), offsets, comm_group, communicator,
+                                std::move(compression_options), /*explicit_copy_to_current_rank=*/true);
+  std::unique_ptr<cudf::table> result = exchange.allocate_communicated_table();
+  exchange.launch_communication(result->mutable_view(), report_timing, preallocated_pinned_buffer);
+  timer.lap("All-to-all communication in shuffle");
+  return result;
 }
