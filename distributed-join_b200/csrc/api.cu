@@ -87,24 +87,14 @@ int sm_count_physical()
   return cached;
 }
 
-namespace {
 
-__global__ void set_two_offsets(int64_t* a, int64_t na, int64_t* b, int64_t nb)
-{
-  a[0] = 0;
-  a[1] = na;
-  b[0] = 0;
-  b[1] = nb;
-}
-
-}  // namespace
-
-// Radix plan shared by both sides of one local join.  A segmented input (a received table:
-// one padded piece per source rank) must go through at least one pass, which also compacts it.
-RadixPlan plan_for(int64_t nbuild, bool any_segmented)
+// Radix plan shared by both sides of one local join.  Every side goes through at least one pass:
+// it is the pass that turns the caller's SoA columns (or the padded per-source pieces of a
+// received table) into the contiguous row-format buckets the join kernel streams.
+RadixPlan plan_for(int64_t nbuild, bool /*any_segmented*/)
 {
   RadixPlan plan = make_radix_plan(nbuild);
-  if (plan.bits1 == 0 && any_segmented) {
+  if (plan.bits1 == 0) {
     plan.bits1    = 1;
     plan.nbuckets = 2;
   }
@@ -117,7 +107,7 @@ size_t side_ws_bytes(int64_t span_rows, const RadixPlan& plan, int nseg)
   const int levels = (plan.bits1 > 0) + (plan.bits2 > 0);
   const int F1 = 1 << plan.bits1, F2 = 1 << plan.bits2;
   size_t total = 4096;
-  total += (size_t)levels * 2 * align_up((size_t)span_rows * 8 + 64, 256);
+  total += (size_t)levels * align_up((size_t)span_rows * sizeof(Row) + 256, 256);
   total += align_up(((size_t)plan.nbuckets + 1) * 8, 256) + align_up(((size_t)F1 + 1) * 8, 256);
   size_t pw = pass_workspace_bytes(1, F1, nseg);
   if (plan.bits2) pw = std::max(pw, pass_workspace_bytes(F1, F2, nseg));
@@ -130,86 +120,82 @@ static size_t local_join_ws_bytes(int64_t nb, int64_t np)
   return side_ws_bytes(nb, plan, 0) + side_ws_bytes(np, plan, 0) + 8192;
 }
 
-// Radix-partitions one side of a join into plan.nbuckets buckets (0, 1 or 2 passes).
+// Radix-partitions one side of a join into plan.nbuckets row-format buckets (1 or 2 passes).
 int prepare_side(const TableInput& in, const RadixPlan& plan, PreparedSide* out, Arena& arena,
                  cudaStream_t stream)
 {
   const int F1 = 1 << plan.bits1, F2 = 1 << plan.bits2;
+  DJ_REQUIRE(plan.bits1 > 0, "inner_join: a radix plan needs at least one level");
   int64_t* off = arena.take<int64_t>((size_t)plan.nbuckets + 1);
-  if (!off) {
+  const size_t pw = std::max(pass_workspace_bytes(1, F1, in.nseg),
+                             plan.bits2 ? pass_workspace_bytes(F1, F2, in.nseg) : (size_t)0);
+  char* pass_ws = arena.take<char>(pw);
+  if (!off || !pass_ws) {
     set_error("inner_join: workspace too small");
     return DJ_ERR_WORKSPACE;
   }
   out->d_off = off;
-  if (plan.bits1 == 0) {
-    set_two_offsets<<<1, 1, 0, stream>>>(off, in.nrows, off, in.nrows);
-    DJ_LAUNCH_CHECK();
-    out->key = in.key;
-    out->pay = in.pay;
-    return DJ_OK;
-  }
-  const size_t pw = std::max(pass_workspace_bytes(1, F1, in.nseg),
-                             plan.bits2 ? pass_workspace_bytes(F1, F2, in.nseg) : (size_t)0);
-  char* pass_ws  = arena.take<char>(pw);
+  auto set_input = [&](PassBuffers& pb) {
+    pb.in_rows = in.rows;
+    pb.in_key  = in.key;
+    pb.in_pay[0] = in.pay;
+    pb.nrows   = in.nrows;
+    if (in.nseg > 0) {
+      pb.d_seg_begin  = in.d_seg_begin;
+      pb.d_seg_end    = in.d_seg_end;
+      pb.d_seg_parent = in.d_seg_parent;
+      pb.nseg         = in.nseg;
+    }
+  };
   if (in.level1_done) {
     // the exchange delivered level-1 buckets as (source, bucket) segments: run level 2 only
-    if (!plan.bits2 || !in.d_seg_parent) {
-      set_error("inner_join: fused level 1 needs a two-level plan");
+    if (!plan.bits2 || !in.d_seg_parent || !in.rows) {
+      set_error("inner_join: fused level 1 needs a two-level plan and row-format pieces");
       return DJ_ERR_ARG;
     }
-    int64_t* k2 = arena.take<int64_t>((size_t)in.nrows + 8);
-    int64_t* p2 = arena.take<int64_t>((size_t)in.nrows + 8);
-    if (!pass_ws || !k2 || !p2) {
+    Row* r2 = arena.take<Row>((size_t)in.nrows + 8);
+    if (!r2) {
       set_error("inner_join: workspace too small");
       return DJ_ERR_WORKSPACE;
     }
     PassDesc d2{1, 0, 0, 32 - plan.bits1 - plan.bits2, F2, F1, 1};
     PassBuffers pb2{};
-    pb2.in_key = in.key; pb2.in_pay[0] = in.pay; pb2.out_key = k2; pb2.out_pay[0] = p2;
-    pb2.nrows = in.nrows; pb2.d_parent_off = nullptr; pb2.d_child_off = off;
-    pb2.d_seg_begin = in.d_seg_begin; pb2.d_seg_end = in.d_seg_end; pb2.d_seg_parent = in.d_seg_parent;
-    pb2.nseg = in.nseg;
+    set_input(pb2);
+    pb2.out_rows = r2;
+    pb2.d_child_off = off;
     int rc2 = run_partition_pass(d2, pb2, pass_ws, pw, stream);
     if (rc2) return rc2;
-    out->key = k2;
-    out->pay = p2;
+    out->rows = r2;
     return DJ_OK;
   }
-  int64_t* k1    = arena.take<int64_t>((size_t)in.nrows + 8);
-  int64_t* p1    = arena.take<int64_t>((size_t)in.nrows + 8);
-  int64_t* off1  = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : off;
-  if (!pass_ws || !k1 || !p1 || !off1) {
+  Row* r1       = arena.take<Row>((size_t)in.nrows + 8);
+  int64_t* off1 = plan.bits2 ? arena.take<int64_t>((size_t)F1 + 1) : off;
+  if (!r1 || !off1) {
     set_error("inner_join: workspace too small");
     return DJ_ERR_WORKSPACE;
   }
   PassDesc d1{1, 0, 0, 32 - plan.bits1, F1, 1, 1};
   PassBuffers pb{};
-  pb.in_key = in.key; pb.in_pay[0] = in.pay; pb.out_key = k1; pb.out_pay[0] = p1;
-  pb.nrows = in.nrows; pb.d_parent_off = nullptr; pb.d_child_off = off1;
-  if (in.nseg > 0) {
-    pb.d_seg_begin = in.d_seg_begin;
-    pb.d_seg_end   = in.d_seg_end;
-    pb.nseg        = in.nseg;
-  }
+  set_input(pb);
+  pb.d_seg_parent = nullptr;  // a first level has a single parent
+  pb.out_rows     = r1;
+  pb.d_child_off  = off1;
   int rc = run_partition_pass(d1, pb, pass_ws, pw, stream);
   if (rc) return rc;
-  out->key = k1;
-  out->pay = p1;
+  out->rows = r1;
   if (plan.bits2) {
-    int64_t* k2 = arena.take<int64_t>((size_t)in.nrows + 8);
-    int64_t* p2 = arena.take<int64_t>((size_t)in.nrows + 8);
-    if (!k2 || !p2) {
+    Row* r2 = arena.take<Row>((size_t)in.nrows + 8);
+    if (!r2) {
       set_error("inner_join: workspace too small");
       return DJ_ERR_WORKSPACE;
     }
     PassDesc d2{1, 0, 0, 32 - plan.bits1 - plan.bits2, F2, F1, 1};
     PassBuffers pb2{};
-    pb2.in_key = k1; pb2.in_pay[0] = p1; pb2.out_key = k2; pb2.out_pay[0] = p2;
+    pb2.in_rows = r1; pb2.out_rows = r2;
     pb2.nrows = in.nrows; pb2.d_parent_off = off1; pb2.d_child_off = off;
     rc = run_partition_pass(d2, pb2, pass_ws, pw, stream);
     if (rc) return rc;
-    out->key = k2;
-    out->pay = p2;
+    out->rows = r2;
   }
   return DJ_OK;
 }
@@ -219,8 +205,8 @@ int join_prepared(const PreparedSide& build, const PreparedSide& probe, const Ra
                   cudaStream_t stream)
 {
   JoinBuffers jb{};
-  jb.bk = build.key; jb.bp = build.pay; jb.d_build_off = build.d_off;
-  jb.pk = probe.key; jb.pp = probe.pay; jb.d_probe_off = probe.d_off;
+  jb.build = build.rows; jb.d_build_off = build.d_off;
+  jb.probe = probe.rows; jb.d_probe_off = probe.d_off;
   jb.nbuckets = plan.nbuckets;
   for (int c = 0; c < 4; c++) jb.out[c] = out[c];
   jb.out_capacity = out_capacity;
@@ -237,7 +223,7 @@ int local_join(const int64_t* bk, const int64_t* bp, int64_t nb, const int64_t* 
 {
   if (nb == 0 || np == 0) return DJ_OK;  // src/distributed_join.cpp:76-82
   const RadixPlan plan = plan_for(nb, false);
-  TableInput tb{bk, bp, nb, nullptr, nullptr, 0}, tp{pk, pp, np, nullptr, nullptr, 0};
+  TableInput tb{bk, bp, nullptr, nb, nullptr, nullptr, 0}, tp{pk, pp, nullptr, np, nullptr, nullptr, 0};
   PreparedSide sb{}, sp{};
   int rc = prepare_side(tb, plan, &sb, arena, stream);
   if (rc) return rc;

@@ -360,13 +360,13 @@ static size_t dist_ws_bytes(int64_t nl, int64_t nr, int world, int odf, double s
   const int nparts = world * odf;
   size_t total     = 1 << 16;
   // partitioned (padded) copies of both tables
-  total += 2 * (align_up((size_t)(nl + (int64_t)nparts * kAlignRows) * 8, 256) +
-                align_up((size_t)(nr + (int64_t)nparts * kAlignRows) * 8, 256));
+  total += align_up((size_t)(nl + (int64_t)nparts * kAlignRows) * sizeof(Row), 256) +
+           align_up((size_t)(nr + (int64_t)nparts * kAlignRows) * sizeof(Row), 256);
   total += 2 * pass_workspace_bytes(1, kMaxFanout) + 4 * align_up(((size_t)kMaxFanout + 1) * 8, 256);
   // receive buffers (balanced estimate with slack) + per-(source, sub-bucket) segment tables
   const size_t rl = (size_t)((double)nl * slack) + (size_t)nparts * kAlignRows + 4096;
   const size_t rr = (size_t)((double)nr * slack) + (size_t)nparts * kAlignRows + 4096;
-  total += 2 * (align_up(rl * 8, 256) + align_up(rr * 8, 256)) + (size_t)odf * 8 * 256 +
+  total += align_up(rl * sizeof(Row), 256) + align_up(rr * sizeof(Row), 256) + (size_t)odf * 8 * 256 +
            (size_t)odf * 2 * 3 * align_up((size_t)kMaxFanout * 8, 256);
   // join scratch for the largest batch (both sides stay alive until the join kernel has run)
   const int64_t bl = (int64_t)(rl / odf) + 4096, br = (int64_t)(rr / odf) + 4096;
@@ -582,21 +582,21 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   const int64_t* in_key[2] = {d_left_key, d_right_key};
   const int64_t* in_pay[2] = {d_left_payload, d_right_payload};
   const size_t pw          = pass_workspace_bytes(1, nbk);
-  int64_t *pk[2], *pp[2], *d_off[2], *d_cnt[2];
+  Row* prow[2];
+  int64_t *d_off[2], *d_cnt[2];
   for (int t = 0; t < 2; t++) {
     char* pws         = arena.take<char>(pw);
     const size_t rows = (size_t)(n_in[t] + (int64_t)nparts * kAlignRows);
-    pk[t]             = arena.take<int64_t>(rows);
-    pp[t]             = arena.take<int64_t>(rows);
+    prow[t]           = arena.take<Row>(rows);
     d_off[t]          = arena.take<int64_t>((size_t)nbk + 1);
     d_cnt[t]          = arena.take<int64_t>((size_t)nbk + 1);
-    if (!pws || !pk[t] || !pp[t] || !d_off[t] || !d_cnt[t]) {
+    if (!pws || !prow[t] || !d_off[t] || !d_cnt[t]) {
       set_error("distributed_inner_join: workspace too small for the partitioned tables");
       return DJ_ERR_WORKSPACE;
     }
     PassDesc desc{sub_bits ? 2 : 0, kNvlinkSeed, DJ_HASH_MURMUR3, 0, nbk, 1, 1, kAlignRows, nparts, sub_bits};
     PassBuffers pb{};
-    pb.in_key = in_key[t]; pb.in_pay[0] = in_pay[t]; pb.out_key = pk[t]; pb.out_pay[0] = pp[t];
+    pb.in_key = in_key[t]; pb.in_pay[0] = in_pay[t]; pb.out_rows = prow[t];
     pb.nrows = n_in[t]; pb.d_child_off = d_off[t]; pb.d_child_cnt = d_cnt[t];
     rc = run_partition_pass(desc, pb, pws, pw, st);
     if (rc) return rc;
@@ -612,7 +612,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   struct Piece {
     std::vector<int64_t> begin, count;  // per source
     int64_t span = 0, rows = 0;
-    int64_t *key = nullptr, *pay = nullptr;
+    Row* data = nullptr;
     int64_t *d_seg_begin = nullptr, *d_seg_end = nullptr;
     int* d_seg_parent = nullptr;
   };
@@ -639,12 +639,9 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     };
     trace.mark(t ? "exchange(R) begin" : "exchange(L) begin", comm->comm_stream);
     // own bucket: device copy (src/all_to_all_comm.cpp:610-653); the rest over NVLink
-    if (pc.count[rank] > 0) {
-      DJ_CUDA_TRY(cudaMemcpyAsync(pc.key + pc.begin[rank], pk[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
-                                  cudaMemcpyDeviceToDevice, comm->comm_stream));
-      DJ_CUDA_TRY(cudaMemcpyAsync(pc.pay + pc.begin[rank], pp[t] + send_begin(rank), (size_t)pc.count[rank] * 8,
-                                  cudaMemcpyDeviceToDevice, comm->comm_stream));
-    }
+    if (pc.count[rank] > 0)
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.data + pc.begin[rank], prow[t] + send_begin(rank),
+                                  (size_t)pc.count[rank] * sizeof(Row), cudaMemcpyDeviceToDevice, comm->comm_stream));
     if (use_peer) {
       // push every peer's bucket into ITS receive piece with the copy engines (no SMs, so the
       // radix passes running meanwhile keep the whole GPU), then raise that peer's flag
@@ -663,10 +660,8 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
             dst_begin += pad_rows(c);
           }
           const int64_t* po = &peer_piece_off[(((size_t)t * world + i) * odf + b) * 2];
-          DJ_CUDA_TRY(cudaMemcpyAsync(peer_ws[i] + po[0] + dst_begin * 8, pk[t] + send_begin(i), (size_t)ns * 8,
-                                      cudaMemcpyDefault, ps));
-          DJ_CUDA_TRY(cudaMemcpyAsync(peer_ws[i] + po[1] + dst_begin * 8, pp[t] + send_begin(i), (size_t)ns * 8,
-                                      cudaMemcpyDefault, ps));
+          DJ_CUDA_TRY(cudaMemcpyAsync(peer_ws[i] + po[0] + dst_begin * sizeof(Row), prow[t] + send_begin(i),
+                                      (size_t)ns * sizeof(Row), cudaMemcpyDefault, ps));
           if (opts) opts->bytes_sent += 16 * ns;
         }
         uint32_t* flag = comm->peer_flags[i] + (size_t)rank * kFlagSlots + slot;
@@ -689,13 +684,13 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       if (i == rank) continue;
       const int64_t ns = send_count(i), nr = pc.count[i];
       if (ns > 0) {
-        DJ_NCCL_TRY(ncclSend(pk[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
-        DJ_NCCL_TRY(ncclSend(pp[t] + send_begin(i), (size_t)ns * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+        DJ_NCCL_TRY(ncclSend(prow[t] + send_begin(i), (size_t)ns * sizeof(Row), ncclInt8, i, comm->nccl,
+                             comm->comm_stream));
         if (opts) opts->bytes_sent += 16 * ns;
       }
       if (nr > 0) {
-        DJ_NCCL_TRY(ncclRecv(pc.key + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
-        DJ_NCCL_TRY(ncclRecv(pc.pay + pc.begin[i], (size_t)nr * 8, ncclInt8, i, comm->nccl, comm->comm_stream));
+        DJ_NCCL_TRY(ncclRecv(pc.data + pc.begin[i], (size_t)nr * sizeof(Row), ncclInt8, i, comm->nccl,
+                             comm->comm_stream));
       }
     }
     DJ_NCCL_TRY(ncclGroupEnd());
@@ -745,7 +740,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
         pc.span += pad_rows(c);
         pc.rows += c;
       }
-      need += 2 * align_up((size_t)pc.span * 8 + 64, 256) + 3 * align_up((size_t)nseg * 8, 256) + 1024;
+      need += align_up((size_t)pc.span * sizeof(Row) + 128, 256) + 3 * align_up((size_t)nseg * 8, 256) + 1024;
       max_span[t] = std::max(max_span[t], pc.span);
     }
     if (t == 1) need += side_ws_bytes(max_span[0], plan, nseg) + side_ws_bytes(max_span[1], plan, nseg) + 4096;
@@ -755,8 +750,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     for (int b = 0; b < odf && fits; b++) {
       const size_t i  = (size_t)b * 2 + t;
       Piece& pc       = pieces[i];
-      pc.key          = arena.take<int64_t>((size_t)pc.span + 8);
-      pc.pay          = arena.take<int64_t>((size_t)pc.span + 8);
+      pc.data         = arena.take<Row>((size_t)pc.span + 8);
       pc.d_seg_begin  = arena.take<int64_t>((size_t)nseg);
       pc.d_seg_end    = arena.take<int64_t>((size_t)nseg);
       pc.d_seg_parent = arena.take<int>((size_t)nseg);
@@ -766,12 +760,12 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       bool ok_local = fits;
       for (int b = 0; b < odf && fits; b++) {
         Piece& pc = pieces[(size_t)b * 2 + t];
-        if (!pc.key || !pc.pay || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) ok_local = false;
+        if (!pc.data || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) ok_local = false;
       }
       mine_off[0] = ok_local ? 1 : 0;
       for (int b = 0; b < odf && ok_local; b++) {
-        mine_off[1 + (size_t)b * 2]     = (char*)pieces[(size_t)b * 2 + t].key - (char*)d_workspace;
-        mine_off[1 + (size_t)b * 2 + 1] = (char*)pieces[(size_t)b * 2 + t].pay - (char*)d_workspace;
+        mine_off[1 + (size_t)b * 2]     = (char*)pieces[(size_t)b * 2 + t].data - (char*)d_workspace;
+        mine_off[1 + (size_t)b * 2 + 1] = 0;
       }
       rc = ctrl_allgather(comm, mine_off.data(), odf * 2 + 1, all_off.data());
       if (rc) return rc;
@@ -865,7 +859,8 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
         }
         trace.mark(t ? "arrived(R)" : "arrived(L)", st);
       }
-      TableInput in{pc.key, pc.pay, pc.span, pc.d_seg_begin, pc.d_seg_end, nseg, pc.d_seg_parent, sub_bits > 0};
+      TableInput in{nullptr, nullptr, pc.data, pc.span, pc.d_seg_begin, pc.d_seg_end, nseg, pc.d_seg_parent,
+                    sub_bits > 0};
       trace.mark(t ? "radix(R) begin" : "radix(L) begin", st);
       rc = prepare_side(in, plan, &side[t], arena, st);
       if (rc) return rc;

@@ -12,6 +12,16 @@ namespace dj {
 constexpr int kMaxPayload = 3;
 constexpr int kMaxFanout  = 1024;
 
+// Internal row format of everything between the caller's SoA columns and the join output:
+// partitioned tables, exchanged pieces, radix levels and the join's inputs are arrays of 16-byte
+// (key, payload) rows.  One row = one 128-bit access, a per-bucket run of rows is one contiguous
+// 16-byte aligned range (a single cp.async.bulk in either direction), and an exchanged bucket is
+// one copy instead of one per column.
+struct __align__(16) Row {
+  int64_t key;
+  int64_t pay;
+};
+
 // Bucket function of one partition pass.
 //   mode 0: (row_hash(key; seed, hash_id)) % F   -- the cuDF-compatible rank partition
 //   mode 1: (local_hash(key) >> shift) & (F-1)   -- the join's private radix sub-partition
@@ -36,6 +46,10 @@ struct PassBuffers {
   const int64_t* in_pay[kMaxPayload];
   int64_t* out_key;
   int64_t* out_pay[kMaxPayload];
+  // Row-format (AoS) input / output; either replaces the SoA pointers of that side.  A pass with
+  // out_rows set runs the row scatter kernel (key + one payload only).
+  const Row* in_rows = nullptr;
+  Row* out_rows      = nullptr;
   int64_t nrows;
   const int64_t* d_parent_off;  // [P+1] absolute row offsets of the parents; nullptr when P == 1
   int64_t* d_child_off;         // [P*F+1] out: absolute row offsets of the child buckets
@@ -56,18 +70,14 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
 // Local join of radix-partitioned tables: bucket b of the build side is rows
 // [d_build_off[b], d_build_off[b+1]) of (bk, bp), likewise for the probe side.
 struct JoinBuffers {
-  const int64_t* bk;
-  const int64_t* bp;
+  const Row* build;
   const int64_t* d_build_off;
-  const int64_t* pk;
-  const int64_t* pp;
+  const Row* probe;
   const int64_t* d_probe_off;
   int nbuckets;
   int64_t* out[4];  // build key, build payload, probe key, probe payload
   int64_t out_capacity;
-  int64_t out_base;        // rows already in the output before this call (batched joins)
   int64_t* d_out_count;    // running total (device); the kernel atomically adds to it
-  int* d_work_counter;     // zeroed by the caller of run_bucket_join
 };
 int run_bucket_join(const JoinBuffers& jb, bool swap_output_sides, cudaStream_t stream);
 
@@ -83,8 +93,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // One side of a local join as it arrives: a contiguous table, or (received tables) `nseg` pieces
 // [d_seg_begin[i], d_seg_end[i]) of arrays spanning `nrows` rows.
 struct TableInput {
-  const int64_t* key;
+  const int64_t* key;  // SoA columns (the caller's table) ...
   const int64_t* pay;
+  const Row* rows;     // ... or rows (a received table); exactly one of the two forms is set
   int64_t nrows;
   const int64_t* d_seg_begin;
   const int64_t* d_seg_end;
@@ -94,8 +105,7 @@ struct TableInput {
 };
 // The same side radix-partitioned for the join: bucket b = rows [d_off[b], d_off[b+1]).
 struct PreparedSide {
-  const int64_t* key;
-  const int64_t* pay;
+  const Row* rows;
   const int64_t* d_off;
 };
 RadixPlan plan_for(int64_t nbuild, bool any_segmented);

@@ -9,10 +9,11 @@
 //                   bulk copies (cp.async.bulk + mbarrier complete_tx): one build-chunk stage
 //                   and a ring of probe-chunk stages, refilled as soon as consumers release them,
 //                   so global-memory latency never sits on the consumers' critical path;
-//   consumer warps  1. insert the staged build rows into a linear-probing table (64-bit key +
-//                      64-bit payload per slot; occupancy bitmap claimed with atomicOr, so no key
-//                      value is reserved as "empty"; two bitmaps ping-pong so the next one is
-//                      cleared off the critical path),
+//   consumer warps  1. insert the staged build rows (16-byte (key, payload) rows, one TMA copy per
+//                      chunk) into a linear-probing table of 32-bit (fingerprint, row) slots claimed
+//                      with atomicCAS -- the staged rows are the row store, no key value is reserved
+//                      as "empty"; two tables ping-pong so the next one is cleared off the critical
+//                      path,
 //                   2. probe one staged row per lane; matches are compacted with __ballot_sync /
 //                      popc into a shared-memory output tile,
 //                   3. flush full output tiles with ONE global atomicAdd per tile and coalesced
@@ -54,11 +55,9 @@ constexpr int kOutTiles    = 3;    // filling / atomicAdd in flight / draining
 constexpr int kDescBuckets = 128;  // bucket descriptors cached per refill
 
 struct JoinDev {
-  const int64_t* bk;
-  const int64_t* bp;
+  const Row* build;
   const int64_t* boff;
-  const int64_t* pk;
-  const int64_t* pp;
+  const Row* probe;
   const int64_t* poff;
   int nbuckets;
   int64_t* out[4];
@@ -69,10 +68,8 @@ struct JoinDev {
 template <class C>
 struct __align__(128) JoinSmem {
   uint32_t slots[2][C::kSlots];
-  int64_t bkey[2][C::kBuildChunk + 2];
-  int64_t bpay[2][C::kBuildChunk + 2];
-  int64_t pkey[C::kProbeStages][C::kProbeChunk + 2];
-  int64_t ppay[C::kProbeStages][C::kProbeChunk + 2];
+  Row brow[2][C::kBuildChunk];
+  Row prow[C::kProbeStages][C::kProbeChunk];
   int64_t sout[kOutTiles][4][C::kOutRows];
   int64_t dboff[kDescBuckets + 1];
   int64_t dpoff[kDescBuckets + 1];
@@ -157,20 +154,16 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
               const int bs = u & 1;
               const int n  = (int)min((int64_t)C::kBuildChunk, b1 - c0);
               mbar_wait(&s.empty_build[bs], ((u >> 1) & 1) ^ 1);
-              const Window wk = window_of(d.bk + c0, n), wp = window_of(d.bp + c0, n);
-              mbar_expect_tx(&s.full_build[bs], wk.bytes + wp.bytes);
-              tma_load(s.bkey[bs], wk.base, wk.bytes, &s.full_build[bs]);
-              tma_load(s.bpay[bs], wp.base, wp.bytes, &s.full_build[bs]);
+              mbar_expect_tx(&s.full_build[bs], (uint32_t)n * 16u);
+              tma_load(s.brow[bs], d.build + c0, (uint32_t)n * 16u, &s.full_build[bs]);
               u++;
             }
             for (int64_t r0 = p0; r0 < p1; r0 += C::kProbeChunk) {
               const int st = q % C::kProbeStages;
               const int n  = (int)min((int64_t)C::kProbeChunk, p1 - r0);
               mbar_wait(&s.empty_probe[st], ((q / C::kProbeStages) & 1) ^ 1);
-              const Window wk = window_of(d.pk + r0, n), wp = window_of(d.pp + r0, n);
-              mbar_expect_tx(&s.full_probe[st], wk.bytes + wp.bytes);
-              tma_load(s.pkey[st], wk.base, wk.bytes, &s.full_probe[st]);
-              tma_load(s.ppay[st], wp.base, wp.bytes, &s.full_probe[st]);
+              mbar_expect_tx(&s.full_probe[st], (uint32_t)n * 16u);
+              tma_load(s.prow[st], d.probe + r0, (uint32_t)n * 16u, &s.full_probe[st]);
               q++;
             }
           }
@@ -187,11 +180,10 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
           const int bs = u & 1;
           const int nb = (int)min((int64_t)C::kBuildChunk, b1 - c0);
           uint32_t* slots     = s.slots[bs];
-          const int64_t* bkey = s.bkey[bs] + skip_of(d.bk + c0);
-          const int64_t* bpay = s.bpay[bs] + skip_of(d.bp + c0);
+          const Row* brow     = s.brow[bs];
           mbar_wait(&s.full_build[bs], (u >> 1) & 1);
           for (int r = tid; r < nb; r += kConsumers) {
-            const uint32_t h = slot_hash_i64(bkey[r]);
+            const uint32_t h = slot_hash_i64(brow[r].key);
             const uint32_t e = (slot_tag(h) << 11) | (uint32_t)r;
             uint32_t slot    = h & (C::kSlots - 1);
             while (atomicCAS(&slots[slot], 0u, e) != 0u) slot = (slot + 1) & (C::kSlots - 1);
@@ -211,8 +203,9 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
             bool alive = tid < np;
             int64_t k = 0, v = 0;
             if (alive) {
-              k = s.pkey[st][skip_of(d.pk + r0) + tid];
-              v = s.ppay[st][skip_of(d.pp + r0) + tid];
+              const int4 pr = *reinterpret_cast<const int4*>(&s.prow[st][tid]);
+              k = (int64_t)(((uint64_t)(uint32_t)pr.y << 32) | (uint32_t)pr.x);
+              v = (int64_t)(((uint64_t)(uint32_t)pr.w << 32) | (uint32_t)pr.z);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.empty_probe[st]);  // rows are in registers: release
@@ -234,7 +227,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
                   }
                   if ((e >> 11) == want) {
                     idx = (int)(e & 0x7ffu);
-                    if (bkey[idx] == k) {
+                    if (brow[idx].key == k) {
                       found = true;
                       break;
                     }
@@ -246,13 +239,18 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
               if (m == 0) break;
               const int leader = __ffs(m) - 1;
               int obase        = 0;
-              if (lane == leader) obase = atomicAdd(&s.scnt[cur], __popc(m));
+              if (lane == leader) {
+                obase = atomicAdd(&s.scnt[cur], __popc(m));
+                // a full tile stays "full": spilled matches are counted by the global counter below, so
+                // pull the tile counter back and keep it from ever wrapping (hot keys: > 2^31 matches)
+                if (obase >= C::kOutRows) atomicSub(&s.scnt[cur], __popc(m));
+              }
               obase         = __shfl_sync(0xffffffffu, obase, leader);
               const int pos = obase + __popc(m & lanemask_lt());
               const bool spill = found && pos >= C::kOutRows;
               if (found && !spill) {
                 s.sout[cur][0][pos] = k;
-                s.sout[cur][1][pos] = bpay[idx];
+                s.sout[cur][1][pos] = brow[idx].pay;
                 s.sout[cur][2][pos] = k;
                 s.sout[cur][3][pos] = v;
               }
@@ -268,7 +266,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) bucket_join_kernel(JoinDev d)
                   const int64_t gi = (int64_t)g + __popc(ms & lanemask_lt());
                   if (gi < d.out_capacity) {
                     d.out[0][gi] = k;
-                    d.out[1][gi] = bpay[idx];
+                    d.out[1][gi] = brow[idx].pay;
                     d.out[2][gi] = k;
                     d.out[3][gi] = v;
                   }
@@ -369,11 +367,9 @@ RadixPlan make_radix_plan(int64_t nbuild)
 int run_bucket_join(const JoinBuffers& jb, bool swap_output_sides, cudaStream_t stream)
 {
   JoinDev d{};
-  d.bk       = jb.bk;
-  d.bp       = jb.bp;
+  d.build    = jb.build;
   d.boff     = jb.d_build_off;
-  d.pk       = jb.pk;
-  d.pp       = jb.pp;
+  d.probe    = jb.probe;
   d.poff     = jb.d_probe_off;
   d.nbuckets = jb.nbuckets;
   for (int c = 0; c < 4; c++) d.out[c] = jb.out[swap_output_sides ? (c + 2) % 4 : c];

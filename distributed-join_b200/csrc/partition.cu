@@ -13,6 +13,14 @@
 //
 // It replaces cudf::hash_partition (reference call sites src/distributed_join.cpp:213-225,
 // src/shuffle_on.cpp:59-60) in mode 0, and is the join's private sub-partitioner in mode 1.
+//
+// Two scatter families:
+//   * SoA -> SoA (scatter_tma_kernel / scatter_kernel): the public cudf::hash_partition
+//     replacement, columns in, columns out.
+//   * -> rows (scatter_rows_kernel): everything internal to the join.  Output is 16-byte
+//     (key, payload) rows; each (tile, bucket) run leaves shared memory as ONE cp.async.bulk
+//     shared->global copy, so the write-out costs no LDS/STG wavefronts at all and overlaps the
+//     ranking of the next tile.  Input is either the caller's SoA columns or rows.
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
@@ -35,6 +43,9 @@ struct PassDev {
   const int64_t* in_pay[kMaxPayload];
   int64_t* out_key;
   int64_t* out_pay[kMaxPayload];
+  const Row* in_rows;        // row-format input (nullptr: SoA in_key / in_pay[0])
+  Row* out_rows;             // row-format output (scatter_rows_kernel)
+  int64_t in_total;          // rows in the input arrays (TMA windows are clamped to the column end)
   const int64_t* seg_begin;  // [S] first row of every input segment
   const int64_t* seg_end;    // [S] one past its last row
   const int* seg_parent;     // [S] output parent bucket the segment's rows belong to
@@ -45,7 +56,6 @@ struct PassDev {
   int S, P, F;
   uint32_t seed;
   int hash_id, shift, pow2;
-  int debug_linear;      // experiments only: write tiles back contiguously (wrong result)
   int nparts, sub_bits;  // mode 2: bucket = (row_hash % nparts) << sub_bits | top sub_bits of local_hash
 };
 
@@ -149,7 +159,7 @@ __global__ void aligned_offsets_kernel(const unsigned long long* counts, int nb,
 }
 
 // ---------------------------------------------------------------- histogram
-template <int MODE>
+template <int MODE, bool IN_ROWS>
 __global__ void __launch_bounds__(kHistThreads) hist_kernel(PassDev d)
 {
   extern __shared__ int s_hist[];
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(PassDev d)
     if (end > d.seg_end[sg]) end = d.seg_end[sg];
 #pragma unroll 8
     for (int64_t i = beg + tid; i < end; i += kHistThreads)
-      atomicAdd(&s_hist[bucket_of<MODE>(d.in_key[i], d)], 1);
+      atomicAdd(&s_hist[bucket_of<MODE>(IN_ROWS ? d.in_rows[i].key : d.in_key[i], d)], 1);
     __syncthreads();
     for (int i = tid; i < d.F; i += kHistThreads) {
       int c = s_hist[i];
@@ -343,16 +353,35 @@ struct TileDesc {
   int parent;
 };
 
-// THREADS x RPT rows per tile, two TMA stages.  RECOMPUTE drops the per-row bucket array of the
-// sorted tile and re-hashes the key when streaming it out (fewer shared-memory wavefronts, more
-// instructions).
-template <int THREADS, int RPT, bool RECOMPUTE>
+// Stages rows [beg, beg+n) of an 8-byte column: the TMA source must be 16-byte aligned, so the copy
+// covers the aligned window around the rows (row `beg` lands at smem_dst[skip_of(col + beg)]).
+// The window never leaves the column: when the column's last row sits in the low half of a
+// 16-byte word, that row is copied by hand instead (a generic-proxy store by the issuing
+// thread, ordered before its mbarrier arrive).  Returns the bytes the TMA will deliver.
+__device__ __forceinline__ uint32_t stage_column(int64_t* smem_dst, const int64_t* col, int64_t beg, int n,
+                                                 int64_t col_rows, unsigned long long* bar, bool issue)
+{
+  const uintptr_t a   = reinterpret_cast<uintptr_t>(col + beg);
+  const uintptr_t lo  = a & ~(uintptr_t)15;
+  uintptr_t hi        = (a + (uintptr_t)n * 8 + 15) & ~(uintptr_t)15;
+  const uintptr_t end = reinterpret_cast<uintptr_t>(col + col_rows);
+  if (hi > end) {
+    hi -= 16;
+    if (issue) smem_dst[(hi - lo) >> 3] = col[beg + n - 1];
+  }
+  const uint32_t bytes = (uint32_t)(hi - lo);
+  if (issue && bytes) tma_load(smem_dst, reinterpret_cast<const void*>(lo), bytes, bar);
+  return bytes;
+}
+
+// THREADS x RPT rows per tile, two TMA stages.
+template <int THREADS, int RPT>
 struct __align__(128) ScatterTmaSmem {
   static constexpr int T = THREADS * RPT;
   int64_t kst[2][T + 2];
   int64_t pst[2][T + 2];
   int4 srow[T];
-  uint16_t sbkt[RECOMPUTE ? 8 : T];
+  uint16_t sbkt[T];
   int s_start[kMaxFanout];
   uint32_t s_delta[kMaxFanout];
   unsigned long long full[2];
@@ -360,10 +389,10 @@ struct __align__(128) ScatterTmaSmem {
   int warp_sums[33];
 };
 
-template <int MODE, bool WARP_AGG, int THREADS, int RPT, bool RECOMPUTE>
-__global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2 > 1 ? 2 : 1) scatter_tma_kernel(PassDev d)
+template <int MODE, bool WARP_AGG, int THREADS, int RPT>
+__global__ void __launch_bounds__(THREADS, 1) scatter_tma_kernel(PassDev d)
 {
-  using Smem = ScatterTmaSmem<THREADS, RPT, RECOMPUTE>;
+  using Smem = ScatterTmaSmem<THREADS, RPT>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& s           = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int T   = THREADS * RPT;
@@ -382,13 +411,13 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2 > 1 ? 2 : 1) scatt
     const int64_t beg = d.seg_begin[prod_parent] + (int64_t)(t - d.scat_tiles[prod_parent]) * T;
     int64_t end       = beg + T;
     if (end > d.seg_end[prod_parent]) end = d.seg_end[prod_parent];
-    const int st = k & 1;
-    s.desc[st]   = TileDesc{beg, (int)(end - beg), d.seg_parent[prod_parent]};
-    const Window wk = window_of(d.in_key + beg, (int)(end - beg));
-    const Window wp = window_of(d.in_pay[0] + beg, (int)(end - beg));
-    mbar_expect_tx(&s.full[st], wk.bytes + wp.bytes);
-    tma_load(s.kst[st], wk.base, wk.bytes, &s.full[st]);
-    tma_load(s.pst[st], wp.base, wp.bytes, &s.full[st]);
+    const int st = k & 1, n = (int)(end - beg);
+    s.desc[st]   = TileDesc{beg, n, d.seg_parent[prod_parent]};
+    const uint32_t bytes = stage_column(s.kst[st], d.in_key, beg, n, d.in_total, &s.full[st], false) +
+                           stage_column(s.pst[st], d.in_pay[0], beg, n, d.in_total, &s.full[st], false);
+    mbar_expect_tx(&s.full[st], bytes);
+    stage_column(s.kst[st], d.in_key, beg, n, d.in_total, &s.full[st], true);
+    stage_column(s.pst[st], d.in_pay[0], beg, n, d.in_total, &s.full[st], true);
   };
 
   if (tid == 0) {
@@ -480,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2 > 1 ? 2 : 1) scatt
         const int64_t pay = pst[r];
         s.srow[pos] = make_int4((int)(uint32_t)(uint64_t)key[j], (int)((uint64_t)key[j] >> 32),
                                 (int)(uint32_t)(uint64_t)pay, (int)((uint64_t)pay >> 32));
-        if (!RECOMPUTE) s.sbkt[pos] = (uint16_t)b;
+        s.sbkt[pos] = (uint16_t)b;
       }
     }
 #pragma unroll
@@ -500,9 +529,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2 > 1 ? 2 : 1) scatt
                      : "=r"(row.x), "=r"(row.y), "=r"(row.z), "=r"(row.w)
                      : "r"(smem_u32(&s.srow[i])));
         const int64_t k64  = (int64_t)(((uint64_t)(uint32_t)row.y << 32) | (uint32_t)row.x);
-        const int b        = RECOMPUTE ? bucket_of<MODE>(k64, d) : (int)s.sbkt[i];
-        uint32_t dst = s.s_delta[b] + (uint32_t)i;
-        if (d.debug_linear) dst = (uint32_t)(td.beg + i);
+        const uint32_t dst = s.s_delta[s.sbkt[i]] + (uint32_t)i;
         d.out_key[dst]     = k64;
         d.out_pay[0][dst]  = (int64_t)(((uint64_t)(uint32_t)row.w << 32) | (uint32_t)row.z);
       }
@@ -510,36 +537,49 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2 > 1 ? 2 : 1) scatt
   }
 }
 
-// ---------------------------------------------------------------- scatter, TMA-staged, in place
-// Same algorithm with the tile sorted IN PLACE inside its single TMA stage: after ranking, the
-// payloads move to their sorted position inside the (already consumed) key array, then the keys
-// (held in registers) move into the payload array.  A CTA needs only 16 B/row of shared memory,
-// so tiles are larger (longer contiguous output runs) and 2-3 CTAs share an SM, hiding each
-// other's load latency and barrier phases.
-template <int THREADS, int RPT>
-struct __align__(128) ScatterInplaceSmem {
+// ---------------------------------------------------------------- scatter -> rows
+// The join's internal partitioner: key + payload in (SoA columns or 16-byte rows), 16-byte rows
+// out.  One persistent 1024-thread CTA per SM; per 4096-row tile:
+//   TMA      the tile arrives in shared memory two tiles ahead (cp.async.bulk + mbarrier);
+//   rank     every row: bucket = hash bits, rank = shared-memory atomicAdd on the bucket's counter
+//            (measured 3.9 cycles per 32 rows at 512-1024 buckets, experiments/mb_smem_rank.cu);
+//   reserve  one thread per bucket: global atomicAdd reserves the run's slice of the bucket (the
+//            result is not needed until the copy-out), block scan of the counters;
+//   sort     every row is written to its bucket-sorted position as one STS.128;
+//   copy-out the thread owning bucket b issues ONE cp.async.bulk shared->global for the run
+//            (16-byte aligned on both sides because rows are 16 bytes): the TMA engine streams the
+//            tile out while the CTA already ranks the next tile.  No LDS/STG for the write-out.
+// Four CTA barriers per tile.  The sorted tile is single-buffered: cp.async.bulk.wait_group.read
+// (shared-memory side of the copies done) is awaited just before the next tile's sort.
+template <int THREADS, int RPT, bool IN_ROWS>
+struct __align__(128) ScatterRowsSmem {
   static constexpr int T = THREADS * RPT;
-  int64_t a[T + 2];  // TMA: keys            -> after the sort: payloads in bucket order
-  int64_t b[T + 2];  // TMA: payloads        -> after the sort: keys in bucket order
+  // input stages: IN_ROWS: Row[2][T]; else int64 key[2][T+2] + pay[2][T+2] (aligned windows)
+  unsigned char in[IN_ROWS ? 2 * T * 16 : 4 * (T + 2) * 8];
+  Row srow[T];
+  int s_cnt[2][kMaxFanout];
   int s_start[kMaxFanout];
-  uint32_t s_delta[kMaxFanout];
-  unsigned long long full;
-  TileDesc desc;
-  int warp_sums[33];
+  unsigned long long full[2];
+  TileDesc desc[2];
+  int warp_sums[32];
 };
 
-template <int MODE, bool WARP_AGG, int THREADS, int RPT, int CTAS>
-__global__ void __launch_bounds__(THREADS, CTAS) scatter_inplace_kernel(PassDev d)
+template <int MODE, bool IN_ROWS, int THREADS, int RPT>
+__global__ void __launch_bounds__(THREADS, 1) scatter_rows_kernel(PassDev d)
 {
-  using Smem = ScatterInplaceSmem<THREADS, RPT>;
+  static_assert(THREADS >= kMaxFanout, "one thread owns one bucket");
+  using Smem = ScatterRowsSmem<THREADS, RPT, IN_ROWS>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem& s           = *reinterpret_cast<Smem*>(smem_raw);
-  constexpr int T   = THREADS * RPT;
-  constexpr int BPT = (kMaxFanout + THREADS - 1) / THREADS;
-  const int tid     = threadIdx.x;
-  const int lane    = tid & 31;
-  const int F       = d.F;
-  const int total   = d.scat_tiles[d.S];
+  Smem& s         = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr int T = THREADS * RPT;
+  const int tid   = threadIdx.x;
+  const int lane  = tid & 31;
+  const int warp  = tid >> 5;
+  const int F     = d.F;
+  const int total = d.scat_tiles[d.S];
+  Row* in_rows    = reinterpret_cast<Row*>(s.in);          // [2][T]
+  int64_t* in_k   = reinterpret_cast<int64_t*>(s.in);      // [2][T+2]
+  int64_t* in_p   = in_k + 2 * (T + 2);                    // [2][T+2]
 
   int prod_parent = 0;
   auto issue_tile = [&](int k) {  // thread 0 only
@@ -549,194 +589,122 @@ __global__ void __launch_bounds__(THREADS, CTAS) scatter_inplace_kernel(PassDev 
     const int64_t beg = d.seg_begin[prod_parent] + (int64_t)(t - d.scat_tiles[prod_parent]) * T;
     int64_t end       = beg + T;
     if (end > d.seg_end[prod_parent]) end = d.seg_end[prod_parent];
-    s.desc          = TileDesc{beg, (int)(end - beg), d.seg_parent[prod_parent]};
-    const Window wk = window_of(d.in_key + beg, (int)(end - beg));
-    const Window wp = window_of(d.in_pay[0] + beg, (int)(end - beg));
-    mbar_expect_tx(&s.full, wk.bytes + wp.bytes);
-    tma_load(s.a, wk.base, wk.bytes, &s.full);
-    tma_load(s.b, wp.base, wp.bytes, &s.full);
+    const int st = k & 1, n = (int)(end - beg);
+    s.desc[st]   = TileDesc{beg, n, d.seg_parent[prod_parent]};
+    if (IN_ROWS) {
+      mbar_expect_tx(&s.full[st], (uint32_t)n * 16u);
+      tma_load(in_rows + (size_t)st * T, d.in_rows + beg, (uint32_t)n * 16u, &s.full[st]);
+    } else {
+      int64_t* ks = in_k + (size_t)st * (T + 2);
+      int64_t* ps = in_p + (size_t)st * (T + 2);
+      const uint32_t bytes = stage_column(ks, d.in_key, beg, n, d.in_total, &s.full[st], false) +
+                             stage_column(ps, d.in_pay[0], beg, n, d.in_total, &s.full[st], false);
+      mbar_expect_tx(&s.full[st], bytes);
+      stage_column(ks, d.in_key, beg, n, d.in_total, &s.full[st], true);
+      stage_column(ps, d.in_pay[0], beg, n, d.in_total, &s.full[st], true);
+    }
   };
 
   if (tid == 0) {
-    mbar_init(&s.full, 1);
+    mbar_init(&s.full[0], 1);
+    mbar_init(&s.full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     issue_tile(0);
+    issue_tile(1);
   }
+  for (int i = tid; i < 2 * kMaxFanout; i += THREADS) (&s.s_cnt[0][0])[i] = 0;
+  __syncthreads();
 
   for (int k = 0; blockIdx.x + k * (int)gridDim.x < total; k++) {
-#pragma unroll
-    for (int q = 0; q < BPT; q++)
-      if (tid + q * THREADS < F) s.s_start[tid + q * THREADS] = 0;
-    __syncthreads();  // histogram cleared; this tile's descriptor visible
-    mbar_wait(&s.full, k & 1);
-    const TileDesc td = s.desc;
+    const int st = k & 1;
+    int* cnt_cur = s.s_cnt[st];
+    mbar_wait(&s.full[st], (k >> 1) & 1);
+    const TileDesc td = s.desc[st];
     const int tile_n  = td.n;
-    const int ska = skip_of(d.in_key + td.beg), skb = skip_of(d.in_pay[0] + td.beg);
 
-    // phase 1: keys -> bucket, rank inside the tile's bucket
-    int64_t key[RPT];
+    // ---- rank
+    int64_t key[RPT], pay[RPT];
     uint32_t brank[RPT];
+    if (IN_ROWS) {
+#pragma unroll
+      for (int j = 0; j < RPT; j++) {
+        const int r = j * THREADS + tid;
+        if (r < tile_n) {
+          const int4 v = *reinterpret_cast<const int4*>(in_rows + (size_t)st * T + r);
+          key[j] = (int64_t)(((uint64_t)(uint32_t)v.y << 32) | (uint32_t)v.x);
+          pay[j] = (int64_t)(((uint64_t)(uint32_t)v.w << 32) | (uint32_t)v.z);
+        } else {
+          key[j] = 0;
+          pay[j] = 0;
+        }
+      }
+    } else {
+      const int64_t* ks = in_k + (size_t)st * (T + 2) + skip_of(d.in_key + td.beg);
+      const int64_t* ps = in_p + (size_t)st * (T + 2) + skip_of(d.in_pay[0] + td.beg);
+#pragma unroll
+      for (int j = 0; j < RPT; j++) {
+        const int r = j * THREADS + tid;
+        key[j]      = r < tile_n ? ks[r] : 0;
+        pay[j]      = r < tile_n ? ps[r] : 0;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
       const int r = j * THREADS + tid;
-      key[j]      = r < tile_n ? s.a[ska + r] : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < RPT; j++) {
-      const int r      = j * THREADS + tid;
-      const bool valid = r < tile_n;
-      const int b      = valid ? bucket_of<MODE>(key[j], d) : 0;
-      int rank;
-      if (WARP_AGG) {
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        rank                 = 0;
-        if (valid) {
-          const unsigned peers = __match_any_sync(vmask, b);
-          const int leader     = __ffs(peers) - 1;
-          int base             = 0;
-          if (lane == leader) base = atomicAdd(&s.s_start[b], __popc(peers));
-          base = __shfl_sync(peers, base, leader);
-          rank = base + __popc(peers & lanemask_lt());
-        }
-      } else {
-        rank = valid ? atomicAdd(&s.s_start[b], 1) : 0;
+      if (r < tile_n) {
+        const int b = bucket_of<MODE>(key[j], d);
+        brank[j]    = ((uint32_t)b << 16) | (uint32_t)atomicAdd(&cnt_cur[b], 1);
       }
-      brank[j] = ((uint32_t)b << 16) | (uint32_t)rank;
     }
-    __syncthreads();  // histogram complete; every key is in registers: array `a` is free
+    __syncthreads();  // (A) tile histogram complete; the input stage has been read
 
-    // phase 2: exclusive scan (BPT consecutive bins per thread) + global slice reservation
-    int cnt[BPT], run[BPT];
-    unsigned long long gres[BPT];
-    {
-      int sum = 0;
-#pragma unroll
-      for (int q = 0; q < BPT; q++) {
-        const int bin = tid * BPT + q;
-        cnt[q]        = bin < F ? s.s_start[bin] : 0;
-        sum += cnt[q];
-      }
-      int excl = block_exclusive_scan<THREADS>(sum, s.warp_sums);
-#pragma unroll
-      for (int q = 0; q < BPT; q++) {
-        const int bin = tid * BPT + q;
-        run[q]        = excl;
-        gres[q]       = 0;
-        if (bin < F) {
-          s.s_start[bin] = excl;
-          if (cnt[q]) gres[q] = atomicAdd(&d.cursor[(size_t)td.parent * F + bin], (unsigned long long)cnt[q]);
-        }
-        excl += cnt[q];
-      }
-    }
-    __syncthreads();
+    if (tid == 0) issue_tile(k + 2);  // refill this stage right away: the rows live in registers
 
-    // phase 3a: payloads to their sorted position inside array `a` (8 rows in flight per thread)
-    // (positions are kept in brank: bucket << 16 | position does not fit, so recompute start)
-    // (brank turns into the sorted position; 4 payloads in flight per thread keep registers low)
+    // ---- reserve + scan (thread b owns bucket b)
+    const int cnt = tid < F ? cnt_cur[tid] : 0;
+    unsigned long long gres = 0;
+    if (cnt) gres = atomicAdd(&d.cursor[(size_t)td.parent * F + tid], (unsigned long long)cnt);
+    if (tid < F) s.s_cnt[st ^ 1][tid] = 0;  // the next tile's counters
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s.warp_sums[warp] = incl;
+    // the previous tile's bulk copies must have read the sorted tile before it is overwritten
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();  // (B)
+    int wbase = lane < warp ? s.warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wbase += __shfl_xor_sync(0xffffffffu, wbase, o);
+    const int excl = wbase + incl - cnt;
+    if (tid < F) s.s_start[tid] = excl;
+    __syncthreads();  // (C)
+
+    // ---- sort: one STS.128 per row
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
       const int r = j * THREADS + tid;
-      brank[j]    = r < tile_n ? (uint32_t)(s.s_start[brank[j] >> 16] + (int)(brank[j] & 0xffffu)) : 0xffffffffu;
-    }
-#pragma unroll
-    for (int j0 = 0; j0 < RPT; j0 += 4) {
-      int64_t pay[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int r = (j0 + j) * THREADS + tid;
-        pay[j]      = (j0 + j < RPT && r < tile_n) ? s.b[skb + r] : 0;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (j0 + j < RPT && brank[j0 + j] != 0xffffffffu) s.a[brank[j0 + j]] = pay[j];
-    }
-#pragma unroll
-    for (int q = 0; q < BPT; q++)
-      if (cnt[q]) s.s_delta[tid * BPT + q] = (uint32_t)gres[q] - (uint32_t)run[q];
-    __syncthreads();  // every payload has left array `b`
-    // phase 3b: keys (registers) to their sorted position inside array `b`
-#pragma unroll
-    for (int j = 0; j < RPT; j++)
-      if (brank[j] != 0xffffffffu) s.b[brank[j]] = key[j];
-    __syncthreads();
-
-    // phase 4: stream the sorted tile out; the bucket is recomputed from the key
-#pragma unroll
-    for (int j = 0; j < RPT; j++) {
-      const int i = j * THREADS + tid;
-      if (i < tile_n) {
-        const int64_t k64 = s.b[i];
-        const int64_t p64 = s.a[i];
-        uint32_t dst      = s.s_delta[bucket_of<MODE>(k64, d)] + (uint32_t)i;
-        if (d.debug_linear) dst = (uint32_t)(td.beg + i);
-        d.out_key[dst]    = k64;
-        d.out_pay[0][dst] = p64;
+      if (r < tile_n) {
+        const int pos = s.s_start[brank[j] >> 16] + (int)(brank[j] & 0xffffu);
+        *reinterpret_cast<int4*>(&s.srow[pos]) =
+          make_int4((int)(uint32_t)(uint64_t)key[j], (int)((uint64_t)key[j] >> 32),
+                    (int)(uint32_t)(uint64_t)pay[j], (int)((uint64_t)pay[j] >> 32));
       }
     }
-    __syncthreads();  // stage fully drained: refill it
-    if (tid == 0) issue_tile(k + 1);
-  }
-}
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> visible to the TMA engine
+    __syncthreads();  // (D) sorted tile complete
 
-// Kernel shape, selectable for experiments with DJ_SCATTER_CFG:
-//   0: 1024 threads x 4 rows, two TMA stages, 1 CTA/SM (default)
-//   2: like 0, bucket recomputed on write-out instead of kept per row
-//   4: sorted in place, 512 threads x 12 rows, one stage, 2 CTAs/SM
-// Measured per 800M-row pass on B200: 0: 7.9 ms, 2: 7.9 ms, 4: 8.0 ms (5.4 ms with contiguous
-// write-out, vs 6.1 ms for 0: the remaining gap is the scattered store stream, not the SM).
-// Shapes with 2048-row tiles (2 CTAs x 512 threads x 4 rows) were 50 % slower.
-int scatter_cfg()
-{
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DJ_SCATTER_CFG");
-    v             = e ? atoi(e) : 0;
-    if (v != 2 && v != 4) v = 0;
+    // ---- copy-out: bucket tid's run [excl, excl+cnt) -> out_rows[gres ...)
+    if (cnt) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d.out_rows + gres),
+                   "r"(smem_u32(&s.srow[excl])), "r"((uint32_t)cnt * 16u)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
-  return v;
-}
-int scatter_tile_rows()
-{
-  return scatter_cfg() == 4 ? 6144 : 4096;
-}
-
-template <int MODE, bool AGG, int THREADS, int RPT, bool RECOMPUTE>
-int launch_scatter_tma_cfg(const PassDev& dev, int ctas_per_sm, cudaStream_t stream)
-{
-  const size_t smem = sizeof(ScatterTmaSmem<THREADS, RPT, RECOMPUTE>);
-  auto kern         = scatter_tma_kernel<MODE, AGG, THREADS, RPT, RECOMPUTE>;
-  DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    ProfScope prof(DJ_PROF_SCATTER, stream);
-    kern<<<sm_count() * ctas_per_sm, THREADS, smem, stream>>>(dev);
-  }
-  DJ_LAUNCH_CHECK();
-  return DJ_OK;
-}
-
-template <int MODE, bool AGG, int THREADS, int RPT, int CTAS>
-int launch_scatter_inplace(const PassDev& dev, cudaStream_t stream)
-{
-  const size_t smem = sizeof(ScatterInplaceSmem<THREADS, RPT>);
-  auto kern         = scatter_inplace_kernel<MODE, AGG, THREADS, RPT, CTAS>;
-  DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    ProfScope prof(DJ_PROF_SCATTER, stream);
-    kern<<<sm_count() * CTAS, THREADS, smem, stream>>>(dev);
-  }
-  DJ_LAUNCH_CHECK();
-  return DJ_OK;
-}
-
-template <int MODE, bool AGG>
-int launch_scatter_tma(const PassDev& dev, cudaStream_t stream)
-{
-  switch (scatter_cfg()) {
-    case 4: return launch_scatter_inplace<MODE, AGG, 512, 12, 2>(dev, stream);
-    case 2: return launch_scatter_tma_cfg<MODE, AGG, 1024, 4, true>(dev, 1, stream);
-    default: return launch_scatter_tma_cfg<MODE, AGG, 1024, 4, false>(dev, 1, stream);
-  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes complete before the CTA exits
 }
 
 bool use_tma_scatter()
@@ -747,6 +715,36 @@ bool use_tma_scatter()
     v             = (e && (e[0] == 'L' || e[0] == 'l')) ? 0 : 1;  // DJ_SCATTER=legacy disables it
   }
   return v == 1;
+}
+
+template <int MODE, bool AGG>
+int launch_scatter_tma(const PassDev& dev, cudaStream_t stream)
+{
+  constexpr int THREADS = 1024, RPT = 4;
+  const size_t smem = sizeof(ScatterTmaSmem<THREADS, RPT>);
+  auto kern         = scatter_tma_kernel<MODE, AGG, THREADS, RPT>;
+  DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof(DJ_PROF_SCATTER, stream);
+    kern<<<sm_count(), THREADS, smem, stream>>>(dev);
+  }
+  DJ_LAUNCH_CHECK();
+  return DJ_OK;
+}
+
+template <int MODE, bool IN_ROWS>
+int launch_scatter_rows(const PassDev& dev, cudaStream_t stream)
+{
+  constexpr int THREADS = 1024, RPT = 4;
+  const size_t smem = sizeof(ScatterRowsSmem<THREADS, RPT, IN_ROWS>);
+  auto kern         = scatter_rows_kernel<MODE, IN_ROWS, THREADS, RPT>;
+  DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof(DJ_PROF_SCATTER, stream);
+    kern<<<sm_count(), THREADS, smem, stream>>>(dev);
+  }
+  DJ_LAUNCH_CHECK();
+  return DJ_OK;
 }
 
 size_t scatter_smem_bytes(int npay, int F)
@@ -779,11 +777,12 @@ int launch_scatter_agg(const PassDev& dev, int F, cudaStream_t stream)
 }
 
 template <int MODE>
-int launch_scatter_npay(const PassDev& dev, int npay, int F, int64_t nrows, cudaStream_t stream)
+int launch_scatter_npay(const PassDev& dev, int npay, int F, int64_t span, cudaStream_t stream)
 {
-  if (npay == 1 && nrows < ((int64_t)1 << 32) && use_tma_scatter())
-    return F <= 32 ? launch_scatter_tma<MODE, true>(dev, stream)
-                   : launch_scatter_tma<MODE, false>(dev, stream);
+  if (dev.out_rows)
+    return dev.in_rows ? launch_scatter_rows<MODE, true>(dev, stream) : launch_scatter_rows<MODE, false>(dev, stream);
+  if (npay == 1 && span < ((int64_t)1 << 32) && use_tma_scatter())
+    return F <= 32 ? launch_scatter_tma<MODE, true>(dev, stream) : launch_scatter_tma<MODE, false>(dev, stream);
   switch (npay) {
     case 1: return launch_scatter_agg<MODE, 1>(dev, F, stream);
     case 2: return launch_scatter_agg<MODE, 2>(dev, F, stream);
@@ -791,6 +790,15 @@ int launch_scatter_npay(const PassDev& dev, int npay, int F, int64_t nrows, cuda
   }
   set_error("partition: unsupported payload column count %d", npay);
   return DJ_ERR_ARG;
+}
+
+template <int MODE>
+void launch_hist(const PassDev& dev, int grid, size_t smem, cudaStream_t stream)
+{
+  if (dev.in_rows)
+    hist_kernel<MODE, true><<<grid, kHistThreads, smem, stream>>>(dev);
+  else
+    hist_kernel<MODE, false><<<grid, kHistThreads, smem, stream>>>(dev);
 }
 
 }  // namespace
@@ -825,6 +833,8 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   DJ_REQUIRE(desc.mode != 1 || (desc.F & (desc.F - 1)) == 0, "radix fan-out must be a power of 2");
   DJ_REQUIRE(desc.mode != 2 || (desc.P == 1 && desc.F == desc.nparts << desc.sub_bits),
              "fused partition: F must be nparts << sub_bits");
+  DJ_REQUIRE(!buf.out_rows || desc.npay == 1, "partition: row output carries exactly one payload column");
+  DJ_REQUIRE(!buf.in_rows || buf.out_rows, "partition: row input needs row output");
   const bool explicit_segs = buf.d_seg_begin != nullptr;
   DJ_REQUIRE(explicit_segs || desc.P == 1 || buf.d_parent_off != nullptr, "partition: parent offsets missing");
   const int S = explicit_segs ? buf.nseg : desc.P;
@@ -847,12 +857,11 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   }
 
   DJ_CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 1) * 8, stream));
-  // 32-bit destination offsets in the TMA kernel: input rows + worst-case padding must fit
+  // 32-bit destination offsets in the SoA TMA kernel: input rows + worst-case padding must fit
   const int64_t span = buf.nrows + (int64_t)nb * desc.align_rows;
-  const bool tma     = desc.npay == 1 && span < ((int64_t)1 << 32) && use_tma_scatter();
   plan_kernel<<<1, 1024, 0, stream>>>(buf.d_parent_off, buf.d_seg_begin, buf.d_seg_end, buf.d_seg_parent,
-                                      buf.nrows, S, tma ? scatter_tile_rows() : kScatterTile, seg_begin,
-                                      seg_end, seg_parent, hist_tiles, scat_tiles);
+                                      buf.nrows, S, kScatterTile, seg_begin, seg_end, seg_parent, hist_tiles,
+                                      scat_tiles);
   DJ_LAUNCH_CHECK();
 
   PassDev dev{};
@@ -862,6 +871,9 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
     dev.in_pay[c]  = buf.in_pay[c];
     dev.out_pay[c] = buf.out_pay[c];
   }
+  dev.in_rows    = buf.in_rows;
+  dev.out_rows   = buf.out_rows;
+  dev.in_total   = buf.nrows;
   dev.seg_begin  = seg_begin;
   dev.seg_end    = seg_end;
   dev.seg_parent = seg_parent;
@@ -877,14 +889,6 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   dev.shift      = desc.shift;
   dev.pow2       = desc.mode == 2 ? (desc.nparts & (desc.nparts - 1)) == 0 : (desc.F & (desc.F - 1)) == 0;
   dev.nparts     = desc.nparts;
-#ifdef DJ_EXPERIMENTS  // measurement aid only (wrong results): contiguous write-out, see DESIGN.md 7.1
-  {
-    const char* e    = getenv("DJ_SCATTER_DEBUG_LINEAR");
-    dev.debug_linear = e && e[0] == '1';
-  }
-#else
-  dev.debug_linear = 0;
-#endif
   dev.sub_bits   = desc.sub_bits;
 
   const int hist_grid = sm_count() * 4;
@@ -892,11 +896,11 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   {
     ProfScope prof(DJ_PROF_HIST, stream);
     if (desc.mode == 0)
-      hist_kernel<0><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
+      launch_hist<0>(dev, hist_grid, hsmem, stream);
     else if (desc.mode == 1)
-      hist_kernel<1><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
+      launch_hist<1>(dev, hist_grid, hsmem, stream);
     else
-      hist_kernel<2><<<hist_grid, kHistThreads, hsmem, stream>>>(dev);
+      launch_hist<2>(dev, hist_grid, hsmem, stream);
   }
   DJ_LAUNCH_CHECK();
 

@@ -230,6 +230,7 @@ ORACLE_API void oracle_multiset_checksum4(const int64_t* c0,
                                           uint64_t* out2)
 {
   uint64_t s1 = 0, s2 = 0;
+#pragma omp parallel for reduction(+ : s1, s2) schedule(static)
   for (int64_t i = 0; i < n; i++) row_digest(c0[i], c1[i], c2[i], c3[i], &s1, &s2);
   out2[0] = s1;
   out2[1] = s2;

@@ -181,6 +181,26 @@ def generate_tables_distributed(g: GenParams, rank: int, world: int):
     return out[0], out[1]
 
 
+def generate_global_tables(g: GenParams, world: int):
+    """The union of every rank's tables after generate_tables_distributed (src/generate_table.cuh:155-272):
+    source rank s contributes rows [0, (n // world) * world) of its local build / probe table.  Generated
+    straight into two global SoA tables (row order is irrelevant to a join).  Returns
+    ((bk, bp), (pk, pp), hits) where hits counts the probe rows drawn as matches."""
+    out, hits = [], 0
+    for which, n in ((0, g.nb), (1, g.np)):
+        per_src = (n // world) * world
+        keys = np.empty(per_src * world, dtype=np.int64)
+        pay = np.empty(per_src * world, dtype=np.int64)
+        for s in range(world):
+            bm = build_bitmap(g, s) if (which == 1 and not g.unique) else None
+            k, p = keys[s * per_src:(s + 1) * per_src], pay[s * per_src:(s + 1) * per_src]
+            h = lib().oracle_generate_rows(C.byref(g), which, s, 0, per_src,
+                                           _p(bm, C.c_uint32) if bm is not None else None, _p(k), _p(p))
+            hits += int(h) if which == 1 else 0
+        out.append((keys, pay))
+    return out[0], out[1], hits
+
+
 def generate_analytical(mult: int, row_begin: int, count: int):
     k = np.empty(count, dtype=np.int64)
     p = np.empty(count, dtype=np.int64)
