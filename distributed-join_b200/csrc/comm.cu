@@ -30,6 +30,7 @@ struct dj_comm {
   cudaStream_t comm_stream = nullptr;
   cudaStream_t ctrl_stream = nullptr;
   cudaEvent_t ev_ready     = nullptr;
+  cudaEvent_t ev_hist      = nullptr;
   cudaEvent_t ev_part[2]   = {nullptr, nullptr};
   cudaEvent_t ev_seg[2]    = {nullptr, nullptr};
   std::vector<cudaEvent_t> ev_batch;
@@ -39,9 +40,15 @@ struct dj_comm {
   bool peer_ok = false;
   uint32_t* d_flags = nullptr;               // [size][kFlagSlots], written by peers
   std::vector<uint32_t*> peer_flags;         // peers' d_flags mapped here
+  int64_t* d_inbox = nullptr;                // [size][kInbox] control messages deposited by peers (same allocation)
+  std::vector<int64_t*> peer_inbox;          // peers' d_inbox mapped here
+  uint32_t cseq = 0;                         // control-message sequence number
   std::vector<cudaStream_t> peer_stream;     // one push stream per peer
   struct IpcEntry { cudaIpcMemHandle_t h; char* base; };
-  std::vector<std::vector<IpcEntry>> ipc_cache;  // per peer: opened workspace allocations
+  std::vector<std::vector<IpcEntry>> ipc_cache;  // per peer: opened workspace allocations (most recent last)
+  std::vector<int64_t> last_handle;              // [size][8] workspace handles seen in the previous call
+  uint32_t** d_peer_flags = nullptr;             // device copy of peer_flags (verdict_kernel)
+  std::vector<cudaEvent_t> ev_xbeg, ev_xend;     // [2][size] timing events around the pushes (measure_exchange)
   uint32_t seq = 0;
   bool flag_by_memcpy = false;
   bool wait_flush = true;  // CU_STREAM_WAIT_VALUE_FLUSH is dropped if the driver refuses it  // fallback when stream write-value is refused on peer memory
@@ -64,7 +71,10 @@ namespace dj {
     }                                                                                         \
   } while (0)
 
-constexpr int kFlagSlots = 64;
+constexpr int kFlagSlots = 64;      // per source rank: data flags 0..61, control inbox flag 62, verdict 63
+constexpr int kCtrlSlot  = kFlagSlots - 2;
+constexpr int kDataSlots = kFlagSlots - 2;
+constexpr int kInbox     = 4096;  // int64 words every source rank may deposit per control message
 constexpr size_t kSmallElems = 1 << 20;  // int64 entries of pinned + device scratch per communicator
 
 static int ensure_events(dj_comm* c, int n)
@@ -83,6 +93,86 @@ using namespace dj;
 
 static int ctrl_allgather(dj_comm* c, const int64_t* h_mine, int n, int64_t* h_all);
 
+static int ensure_xevents(dj_comm* c, int n)
+{
+  while ((int)c->ev_xbeg.size() < n) {
+    cudaEvent_t a, b;
+    DJ_CUDA_TRY(cudaEventCreate(&a));
+    DJ_CUDA_TRY(cudaEventCreate(&b));
+    c->ev_xbeg.push_back(a);
+    c->ev_xend.push_back(b);
+  }
+  return DJ_OK;
+}
+
+// The stream waits until *d_flag >= value (a peer raises it over NVLink).
+static int stream_wait_flag(dj_comm* c, cudaStream_t st, const uint32_t* d_flag, uint32_t value)
+{
+  const CUdeviceptr fa = (CUdeviceptr)d_flag;
+  CUresult wr          = CUDA_ERROR_NOT_SUPPORTED;
+  if (c->wait_flush) {
+    wr = c->fn_wait32((CUstream)st, fa, value, CU_STREAM_WAIT_VALUE_GEQ | CU_STREAM_WAIT_VALUE_FLUSH);
+    if (wr != CUDA_SUCCESS) c->wait_flush = false;
+  }
+  if (wr != CUDA_SUCCESS) wr = c->fn_wait32((CUstream)st, fa, value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (wr != CUDA_SUCCESS) {
+    set_error("distributed_inner_join: cuStreamWaitValue32 failed with CUresult %d", (int)wr);
+    return DJ_ERR_CUDA;
+  }
+  return DJ_OK;
+}
+
+// Control-plane all-gather WITHOUT kernels: every rank deposits `n` int64 words (device or pinned host
+// memory) into every peer's inbox with copy-engine copies over NVLink, raises the peer's control
+// flag with a stream memory operation, waits for the peers' flags and reads its inbox back.  Unlike
+// an NCCL collective it needs no SM, so it is never held up by the persistent partition / join
+// kernels that fill the GPU (an NCCL all-gather issued next to them waited for a kernel boundary:
+// 4.1 ms measured at N=2).  Safe to reuse the single inbox every call: a rank leaves a join only
+// after every peer has published its verdict, i.e. long after all inboxes of that call were read.
+static int peer_allgather(dj_comm* c, const void* src, int n, int64_t* h_all)
+{
+  DJ_REQUIRE(n >= 1 && n <= kInbox, "control message of %d words exceeds the inbox", n);
+  cudaStream_t st    = c->ctrl_stream;
+  const uint32_t seq = ++c->cseq;
+  for (int i = 0; i < c->size; i++) {
+    DJ_CUDA_TRY(cudaMemcpyAsync(c->peer_inbox[i] + (size_t)c->rank * kInbox, src, (size_t)n * 8, cudaMemcpyDefault, st));
+    if (i == c->rank) continue;
+    uint32_t* flag = c->peer_flags[i] + (size_t)c->rank * kFlagSlots + kCtrlSlot;
+    if (!c->flag_by_memcpy && c->fn_write32((CUstream)st, (CUdeviceptr)flag, seq, 0) != CUDA_SUCCESS)
+      c->flag_by_memcpy = true;
+    if (c->flag_by_memcpy) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(c->h_pinned + (910 << 10)) + (seq % 4096);
+      *w          = seq;
+      DJ_CUDA_TRY(cudaMemcpyAsync(flag, w, 4, cudaMemcpyDefault, st));
+    }
+  }
+  for (int srcr = 0; srcr < c->size; srcr++) {
+    if (srcr == c->rank) continue;
+    int rc = stream_wait_flag(c, st, c->d_flags + (size_t)srcr * kFlagSlots + kCtrlSlot, seq);
+    if (rc) return rc;
+  }
+  int64_t* land = c->h_pinned + (512 << 10);  // [size][n]
+  DJ_REQUIRE((size_t)n * c->size <= (256u << 10), "control message too large for the landing zone");
+  DJ_CUDA_TRY(cudaMemcpy2DAsync(land, (size_t)n * 8, c->d_inbox, (size_t)kInbox * 8, (size_t)n * 8, c->size,
+                                cudaMemcpyDeviceToHost, st));
+  DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(h_all, land, (size_t)n * c->size * 8);
+  return DJ_OK;
+}
+
+// One thread: this rank's overflow verdict goes into every peer's flag block (slot `slot` of row
+// `rank`) as (seq << 1) | overflowed, with system-scope release stores over NVLink.
+__global__ void verdict_kernel(const unsigned long long* d_count, unsigned long long capacity,
+                               uint32_t* const* peer_flags, int world, int rank, int slots, int slot, uint32_t seq)
+{
+  if (threadIdx.x != 0) return;
+  const uint32_t v = (seq << 1) | (*d_count > capacity ? 1u : 0u);
+  for (int p = 0; p < world; p++) {
+    uint32_t* f = peer_flags[p] + (size_t)rank * slots + slot;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(v) : "memory");
+  }
+}
+
 // Maps every peer's flag block; decides (collectively) whether the copy-engine exchange is usable.
 static int setup_peer_exchange(dj_comm* c)
 {
@@ -100,8 +190,11 @@ static int setup_peer_exchange(dj_comm* c)
   c->fn_addr_range = (decltype(c->fn_addr_range))fn;
   cudaGetLastError();
 
-  DJ_CUDA_TRY(cudaMalloc(&c->d_flags, (size_t)c->size * kFlagSlots * sizeof(uint32_t)));
-  DJ_CUDA_TRY(cudaMemset(c->d_flags, 0, (size_t)c->size * kFlagSlots * sizeof(uint32_t)));
+  const size_t flag_bytes = align_up((size_t)c->size * kFlagSlots * sizeof(uint32_t), 256);
+  const size_t ctl_bytes  = flag_bytes + (size_t)c->size * kInbox * sizeof(int64_t);
+  DJ_CUDA_TRY(cudaMalloc(&c->d_flags, ctl_bytes));
+  DJ_CUDA_TRY(cudaMemset(c->d_flags, 0, ctl_bytes));
+  c->d_inbox = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(c->d_flags) + flag_bytes);
   cudaIpcMemHandle_t mine;
   if (cudaIpcGetMemHandle(&mine, c->d_flags) != cudaSuccess) {
     ok = false;
@@ -116,6 +209,7 @@ static int setup_peer_exchange(dj_comm* c)
   if (rc) return rc;
   for (int r = 0; r < c->size; r++) ok = ok && all[(size_t)r * 9] == 1;
   c->peer_flags.assign(c->size, nullptr);
+  c->peer_inbox.assign(c->size, nullptr);
   c->peer_stream.assign(c->size, nullptr);
   c->ipc_cache.assign(c->size, {});
   int64_t opened = 1;
@@ -123,6 +217,7 @@ static int setup_peer_exchange(dj_comm* c)
     for (int r = 0; r < c->size; r++) {
       if (r == c->rank) {
         c->peer_flags[r] = c->d_flags;
+        c->peer_inbox[r] = c->d_inbox;
         continue;
       }
       cudaIpcMemHandle_t h;
@@ -134,6 +229,7 @@ static int setup_peer_exchange(dj_comm* c)
         break;
       }
       c->peer_flags[r] = (uint32_t*)p;
+      c->peer_inbox[r] = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(p) + flag_bytes);
       DJ_CUDA_TRY(cudaStreamCreateWithFlags(&c->peer_stream[r], cudaStreamNonBlocking));
     }
   }
@@ -141,6 +237,11 @@ static int setup_peer_exchange(dj_comm* c)
   rc = ctrl_allgather(c, &opened, 1, oks.data());
   if (rc) return rc;
   for (int r = 0; r < c->size; r++) ok = ok && oks[r] == 1;
+  if (ok) {
+    DJ_CUDA_TRY(cudaMalloc(&c->d_peer_flags, (size_t)c->size * sizeof(uint32_t*)));
+    DJ_CUDA_TRY(cudaMemcpy(c->d_peer_flags, c->peer_flags.data(), (size_t)c->size * sizeof(uint32_t*),
+                           cudaMemcpyHostToDevice));
+  }
   c->peer_ok = ok;
   return DJ_OK;
 }
@@ -148,8 +249,20 @@ static int setup_peer_exchange(dj_comm* c)
 // Peer view of rank `peer`'s workspace allocation described by (handle, offset); opened once.
 static char* map_peer_workspace(dj_comm* c, int peer, const cudaIpcMemHandle_t& h, int64_t offset)
 {
-  for (auto& e : c->ipc_cache[peer])
-    if (memcmp(&e.h, &h, sizeof(h)) == 0) return e.base + offset;
+  auto& cache = c->ipc_cache[peer];
+  for (size_t i = 0; i < cache.size(); i++)
+    if (memcmp(&cache[i].h, &h, sizeof(h)) == 0) {
+      const dj_comm::IpcEntry e = cache[i];
+      cache.erase(cache.begin() + i);
+      cache.push_back(e);  // most recently used last
+      return e.base + offset;
+    }
+  // a peer rarely alternates between more than two live workspaces: older mappings are closed so
+  // that the memory behind them can really be released by its owner
+  while (cache.size() >= 2) {
+    cudaIpcCloseMemHandle(cache.front().base);
+    cache.erase(cache.begin());
+  }
   void* p = nullptr;
   if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
     cudaGetLastError();
@@ -185,6 +298,7 @@ extern "C" int dj_comm_create(int rank, int size, const void* h_id128, dj_comm_t
   DJ_CUDA_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   DJ_CUDA_TRY(cudaStreamCreateWithFlags(&c->ctrl_stream, cudaStreamNonBlocking));
   DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_hist, cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) {
     DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_part[i], cudaEventDisableTiming));
     DJ_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_seg[i], cudaEventDisableTiming));
@@ -218,6 +332,10 @@ extern "C" int dj_comm_destroy(dj_comm_t* c)
   for (auto& v : c->ipc_cache)
     for (auto& e : v) cudaIpcCloseMemHandle(e.base);
   if (c->d_flags) cudaFree(c->d_flags);
+  if (c->d_peer_flags) cudaFree(c->d_peer_flags);
+  for (auto e : c->ev_xbeg) cudaEventDestroy(e);
+  for (auto e : c->ev_xend) cudaEventDestroy(e);
+  if (c->ev_hist) cudaEventDestroy(c->ev_hist);
   for (auto e : c->ev_batch) cudaEventDestroy(e);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -225,6 +343,24 @@ extern "C" int dj_comm_destroy(dj_comm_t* c)
   if (c->d_small) cudaFree(c->d_small);
   delete c;
   return DJ_OK;
+}
+
+// Collective: every rank closes its mappings of the peers' workspaces, then all ranks meet, so that
+// a caller may cudaFree / shrink / regrow its workspace afterwards (freeing memory that an importer
+// still has open is undefined behaviour in CUDA IPC).
+extern "C" int dj_comm_release_workspace(dj_comm_t* c)
+{
+  if (!c || c->size == 1) return DJ_OK;
+  cudaDeviceSynchronize();
+  for (auto& v : c->ipc_cache) {
+    for (auto& e : v) cudaIpcCloseMemHandle(e.base);
+    v.clear();
+  }
+  c->last_handle.clear();
+  cudaGetLastError();
+  int64_t one = 1;
+  std::vector<int64_t> all(c->size);
+  return ctrl_allgather(c, &one, 1, all.data());
 }
 
 extern "C" int dj_comm_rank(const dj_comm_t* c) { return c ? c->rank : 0; }
@@ -271,6 +407,17 @@ static int ctrl_allgather(dj_comm* c, const int64_t* h_mine, int n, int64_t* h_a
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(h_all, hs + n, (size_t)n * c->size * 8);
   return DJ_OK;
+}
+
+// Control all-gather of host words: kernel-free peer path when available, NCCL otherwise.
+static int ctrl_gather_host(dj_comm* c, const int64_t* h_mine, int n, int64_t* h_all)
+{
+  if (c->size > 1 && c->peer_ok && n <= kInbox) {
+    int64_t* stage = c->h_pinned + (129 << 10);  // pinned copy: the source must outlive the async copies
+    memcpy(stage, h_mine, (size_t)n * 8);
+    return peer_allgather(c, stage, n, h_all);
+  }
+  return ctrl_allgather(c, h_mine, n, h_all);
 }
 
 extern "C" int dj_comm_barrier(dj_comm_t* c, void* stream)
@@ -347,6 +494,13 @@ extern "C" int dj_all_to_all(dj_comm_t* c, int group_size, const int* h_group_ra
 // ------------------------------------------------------------------------- distributed join
 
 static const uint32_t kNvlinkSeed = 12345678u;  // src/distributed_join.cpp:211
+
+// Which side the hash tables are built on.  The caller's LEFT table is the build side (the reference's
+// drivers pass the unique-key build table as `left`, benchmark/distributed_join.cu:266-283) unless the
+// right table is clearly smaller: received slices of equal-sized tables differ by a few rows per rank,
+// and letting that noise pick the side made some ranks build on the duplicate-laden probe table
+// (measured at N=2: 11.2 ms instead of 7.9 ms for the same join).
+static inline bool build_on_right(int64_t nleft, int64_t nright) { return nright + nright / 8 < nleft; }
 // Buckets handed to NCCL start on 32-row (256-byte) boundaries on both the send and the receive
 // side: NCCL's peer copies drop to narrow accesses on pointers that are not 16-byte aligned (the
 // reference works around the same effect with two staging copies, src/communicator.cpp:820-869).
@@ -451,6 +605,8 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   if (opts) {
     opts->t_partition_ms = opts->t_comm_ms = opts->t_join_ms = 0;
     opts->bytes_sent = 0;
+    opts->workspace_needed = 0;
+    opts->t_exchange_ms[0] = opts->t_exchange_ms[1] = 0;
   }
   Arena arena(d_workspace, workspace_bytes);
   int64_t* d_count = arena.take<int64_t>(32);
@@ -461,7 +617,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
 
   if (world == 1) {
     // src/distributed_join.cpp:186-199 -- one rank: the local join is the whole job.
-    const bool swap = nright < nleft;  // build on the smaller table
+    const bool swap = build_on_right(nleft, nright);
     int rc = swap ? local_join(d_right_key, d_right_payload, nright, d_left_key, d_left_payload,
                                nleft, out, out_capacity, d_count, true, arena, st)
                   : local_join(d_left_key, d_left_payload, nleft, d_right_key, d_right_payload,
@@ -485,38 +641,57 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   const int G      = world;  // one NVSwitch box: the NVLink group is every rank
   const int nparts = G * odf;
   DJ_REQUIRE(nparts <= kMaxFanout, "distributed_inner_join: %d partitions exceed %d", nparts, kMaxFanout);
-  DJ_REQUIRE(nleft < ((int64_t)1 << 31) && nright < ((int64_t)1 << 31),
-             "distributed_inner_join: per-rank tables are limited to 2^31 rows");
+  DJ_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "distributed_inner_join: the workspace must be 256-byte aligned");
   int rc = ensure_events(comm, 2 * odf);
   if (rc) return rc;
   Trace trace;
   trace.init(st);
-  // The persistent partition / join kernels leave a couple of SMs idle for the whole call: the
-  // control plane's tiny NCCL all-gathers are kernels too, and a GPU saturated by persistent CTAs
-  // would make each of them wait for a kernel boundary (measured: up to 4 ms per collective).
+  // NCCL fallback only: the persistent partition / join kernels leave a couple of SMs idle for the
+  // whole call, because the control plane's tiny NCCL all-gathers are kernels too and a GPU
+  // saturated by persistent CTAs makes each of them wait for a kernel boundary (measured: up to
+  // 4 ms per collective).  The default control plane moves its messages with copy engines.
   struct ReserveGuard {
-    ReserveGuard()
+    explicit ReserveGuard(int dflt)
     {
       const char* e = getenv("DJ_SM_RESERVE");
-      set_sm_reserve(e ? atoi(e) : 2);
+      set_sm_reserve(e ? atoi(e) : dflt);
     }
     ~ReserveGuard() { set_sm_reserve(0); }
-  } reserve_guard;
+  } reserve_guard(comm->peer_ok ? 0 : 2);  // the peer-memory control plane launches no kernels
 
-  // ---- 0. agree on the join's radix plan from the global table sizes.  When the plan has two
-  //         levels, the first one is FUSED into the rank partition on the sender: bucket =
-  //         (destination, sub-bucket), so the receiver only runs the second level.
+  // ---- 0. ONE control all-gather opens the call: table sizes (-> the radix plan every rank derives
+  //         identically), workspace size, and the CUDA IPC identity of the workspace.  Everything a
+  //         rank later needs to know about a peer's memory layout follows from these numbers and
+  //         from the bucket-count matrix (step 2) by pure arithmetic -- no further agreement rounds.
+  constexpr int kHello = 13;  // nleft, nright, workspace bytes, ipc ok, offset in allocation, handle[8]
+  std::vector<int64_t> hello((size_t)world * kHello);
+  {
+    int64_t mine[kHello] = {nleft, nright, (int64_t)workspace_bytes, 0, 0};
+    if (comm->peer_ok) {
+      CUdeviceptr base = 0;
+      size_t alloc_sz  = 0;
+      cudaIpcMemHandle_t wh;
+      memset(&wh, 0, sizeof(wh));
+      const bool ok = comm->fn_addr_range(&base, &alloc_sz, (CUdeviceptr)d_workspace) == CUDA_SUCCESS &&
+                      cudaIpcGetMemHandle(&wh, (void*)base) == cudaSuccess;
+      cudaGetLastError();
+      mine[3] = ok ? 1 : 0;
+      mine[4] = ok ? (int64_t)((CUdeviceptr)d_workspace - base) : 0;
+      memcpy(&mine[5], &wh, 64);
+    }
+    rc = ctrl_gather_host(comm, mine, kHello, hello.data());
+    if (rc) return rc;
+  }
+  auto H = [&](int r, int f) -> int64_t { return hello[(size_t)r * kHello + f]; };
   int sub_bits = 0;
   RadixPlan plan{0, 0, 1};
   {
-    int64_t sizes[2] = {nleft, nright};
-    std::vector<int64_t> alls((size_t)world * 2);
-    rc = ctrl_allgather(comm, sizes, 2, alls.data());
-    if (rc) return rc;
     int64_t tot[2] = {0, 0};
     for (int r = 0; r < world; r++) {
-      tot[0] += alls[(size_t)r * 2];
-      tot[1] += alls[(size_t)r * 2 + 1];
+      DJ_REQUIRE(H(r, 0) < ((int64_t)1 << 31) && H(r, 1) < ((int64_t)1 << 31),
+                 "distributed_inner_join: per-rank tables are limited to 2^31 rows (rank %d)", r);
+      tot[0] += H(r, 0);
+      tot[1] += H(r, 1);
     }
     const int64_t est_build = std::min(tot[0], tot[1]) / nparts + 1;  // rows per rank and batch
     plan                    = plan_for(est_build, true);
@@ -533,82 +708,197 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       }
     }
   }
-  trace.host("plan agreed");
-  // ---- 0b. copy-engine exchange: map every peer's workspace for this call (cached per allocation)
-  bool use_peer = comm->peer_ok && 2 * odf <= kFlagSlots;
+  trace.host("hello gathered, plan agreed");
+
+  const int F1s  = 1 << sub_bits;       // sub-buckets per destination in the sender's partition
+  const int nbk  = nparts << sub_bits;  // buckets of the sender's partition
+  const int nseg = G * F1s;             // (source, sub-bucket) segments of a received piece
+  const size_t pw = pass_workspace_bytes(1, nbk);
+
+  // Workspace layout of ANY rank, as offsets from its workspace base: a pure function of that
+  // rank's table sizes and (for the receive pieces) of the rows it receives -- so every rank can
+  // compute where its rows go inside every peer without asking.
+  struct WsLayout {
+    size_t count = 0, pws[2] = {0, 0}, prow[2] = {0, 0}, doff[2] = {0, 0}, dcnt[2] = {0, 0};
+    std::vector<size_t> piece, seg_begin, seg_end, seg_parent;  // [odf*2]
+    size_t join_mark = 0, need = 0;
+  };
+  auto off_of = [](const void* p) { return (size_t)reinterpret_cast<uintptr_t>(p); };
+  auto lay_out = [&](int64_t nl, int64_t nr, const int64_t* spans /* [odf*2], nullptr: partition part only */) {
+    WsLayout L;
+    Arena va(nullptr, ~(size_t)0 >> 1);
+    L.count = off_of(va.take<int64_t>(32));
+    const int64_t n2[2] = {nl, nr};
+    for (int t = 0; t < 2; t++) {
+      L.pws[t]  = off_of(va.take<char>(pw));
+      L.prow[t] = off_of(va.take<Row>((size_t)(n2[t] + (int64_t)nparts * kAlignRows)));
+      L.doff[t] = off_of(va.take<int64_t>((size_t)nbk + 1));
+    }
+    L.dcnt[0] = off_of(va.take<int64_t>((size_t)2 * nbk + 2));  // both tables' counts, contiguous: one message
+    L.dcnt[1] = L.dcnt[0] + (size_t)nbk * 8;
+    L.need = va.used;
+    if (!spans) return L;
+    L.piece.resize((size_t)odf * 2);
+    L.seg_begin.resize((size_t)odf * 2);
+    L.seg_end.resize((size_t)odf * 2);
+    L.seg_parent.resize((size_t)odf * 2);
+    int64_t max_span[2] = {0, 0};
+    for (int t = 0; t < 2; t++)
+      for (int b = 0; b < odf; b++) {
+        const size_t i  = (size_t)b * 2 + t;
+        L.piece[i]      = off_of(va.take<Row>((size_t)spans[i] + 8));
+        L.seg_begin[i]  = off_of(va.take<int64_t>((size_t)nseg));
+        L.seg_end[i]    = off_of(va.take<int64_t>((size_t)nseg));
+        L.seg_parent[i] = off_of(va.take<int>((size_t)nseg));
+        max_span[t]     = std::max(max_span[t], spans[i]);
+      }
+    L.join_mark = va.used;
+    L.need      = va.used + side_ws_bytes(max_span[0], plan, nseg) + side_ws_bytes(max_span[1], plan, nseg) + 4096;
+    return L;
+  };
+  // every rank checks every rank's partition-stage fit: the verdict is identical everywhere
+  for (int r = 0; r < world; r++) {
+    const WsLayout L = lay_out(H(r, 0), H(r, 1), nullptr);
+    if (L.need > (size_t)H(r, 2)) {
+      if (opts) opts->workspace_needed = (int64_t)lay_out(nleft, nright, nullptr).need;
+      set_error("distributed_inner_join: workspace too small on rank %d for the partitioned tables (%zu of %lld bytes)",
+                r, L.need, (long long)H(r, 2));
+      return DJ_ERR_WORKSPACE;
+    }
+  }
+
+  // ---- 0b. copy-engine exchange: map every peer's workspace (cached per allocation; a peer whose
+  //          allocation changed since the last call has its old mapping closed first)
+  bool use_peer = comm->peer_ok && 2 * odf <= kDataSlots;
+  for (int r = 0; r < world; r++) use_peer = use_peer && H(r, 3) == 1;
   std::vector<char*> peer_ws(world, nullptr);
   if (use_peer) {
-    CUdeviceptr base = 0;
-    size_t alloc_sz  = 0;
-    cudaIpcMemHandle_t wh;
-    memset(&wh, 0, sizeof(wh));
-    bool ok = comm->fn_addr_range(&base, &alloc_sz, (CUdeviceptr)d_workspace) == CUDA_SUCCESS &&
-              cudaIpcGetMemHandle(&wh, (void*)base) == cudaSuccess;
-    cudaGetLastError();
-    std::vector<int64_t> send(10), allh((size_t)world * 10);
-    send[0] = ok ? 1 : 0;
-    send[1] = ok ? (int64_t)((CUdeviceptr)d_workspace - base) : 0;
-    memcpy(&send[2], &wh, 64);
-    rc = ctrl_allgather(comm, send.data(), 10, allh.data());
-    if (rc) return rc;
-    for (int r = 0; r < world; r++) ok = ok && allh[(size_t)r * 10] == 1;
+    bool any_new = false;  // identical on every rank: everybody sees the same handles
+    if (comm->last_handle.size() != (size_t)world * 8) {
+      comm->last_handle.assign((size_t)world * 8, 0);
+      any_new = true;
+    }
+    for (int r = 0; r < world; r++)
+      if (memcmp(&comm->last_handle[(size_t)r * 8], &hello[(size_t)r * kHello + 5], 64) != 0) any_new = true;
     int64_t mapped = 1;
-    if (ok)
-      for (int r = 0; r < world && mapped; r++) {
-        if (r == rank) continue;
-        cudaIpcMemHandle_t h;
-        memcpy(&h, &allh[(size_t)r * 10 + 2], 64);
-        peer_ws[r] = map_peer_workspace(comm, r, h, allh[(size_t)r * 10 + 1]);
-        if (!peer_ws[r]) mapped = 0;
-      }
-    std::vector<int64_t> oks(world);
-    rc = ctrl_allgather(comm, &mapped, 1, oks.data());
-    if (rc) return rc;
-    for (int r = 0; r < world; r++) ok = ok && oks[r] == 1;
-    use_peer = ok;  // identical on every rank; otherwise fall back to the NCCL exchange
+    for (int r = 0; r < world && mapped; r++) {
+      if (r == rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &hello[(size_t)r * kHello + 5], 64);
+      peer_ws[r] = map_peer_workspace(comm, r, h, H(r, 4));
+      if (!peer_ws[r]) mapped = 0;
+    }
+    if (any_new) {
+      // a mapping was (re)opened somewhere: agree that it worked before anybody pushes
+      std::vector<int64_t> oks(world);
+      rc = ctrl_gather_host(comm, &mapped, 1, oks.data());
+      if (rc) return rc;
+      for (int r = 0; r < world; r++) use_peer = use_peer && oks[r] == 1;
+      for (int r = 0; r < world; r++) memcpy(&comm->last_handle[(size_t)r * 8], &hello[(size_t)r * kHello + 5], 64);
+    } else if (!mapped) {
+      set_error("distributed_inner_join: a cached peer mapping disappeared");
+      return DJ_ERR_CUDA;
+    }
   }
   trace.host("peer workspaces mapped");
   const uint32_t seq = use_peer ? ++comm->seq : 0;
-  std::vector<int64_t> peer_piece_off;  // [table][rank][batch][key|pay] byte offsets in the peer's workspace
-  peer_piece_off.assign((size_t)2 * world * odf * 2, 0);
 
-  const int F1s = 1 << sub_bits;       // sub-buckets per destination in the sender's partition
-  const int nbk = nparts << sub_bits;  // buckets of the sender's partition
-  const int nseg = G * F1s;            // (source, sub-bucket) segments of a received piece
-
-  // ---- 1. hash partition both tables (src/distributed_join.cpp:213-225) on the caller's stream;
-  //         every destination's run of buckets starts on kAlignRows so NCCL sends straight from it
+  // ---- 1. hash partition (src/distributed_join.cpp:213-225) on the caller's stream, as histogram
+  //         halves first: the counts of BOTH tables leave for the host while the scatter kernels run.
+  //         Every destination's run of buckets starts on kAlignRows so pushes go straight from it.
+  const WsLayout my = lay_out(nleft, nright, nullptr);
+  char* wsb         = (char*)d_workspace;
   const int64_t n_in[2]    = {nleft, nright};
   const int64_t* in_key[2] = {d_left_key, d_right_key};
   const int64_t* in_pay[2] = {d_left_payload, d_right_payload};
-  const size_t pw          = pass_workspace_bytes(1, nbk);
   Row* prow[2];
-  int64_t *d_off[2], *d_cnt[2];
+  int64_t* d_cnt[2];
+  PassState pstate[2];
   for (int t = 0; t < 2; t++) {
-    char* pws         = arena.take<char>(pw);
-    const size_t rows = (size_t)(n_in[t] + (int64_t)nparts * kAlignRows);
-    prow[t]           = arena.take<Row>(rows);
-    d_off[t]          = arena.take<int64_t>((size_t)nbk + 1);
-    d_cnt[t]          = arena.take<int64_t>((size_t)nbk + 1);
-    if (!pws || !prow[t] || !d_off[t] || !d_cnt[t]) {
-      set_error("distributed_inner_join: workspace too small for the partitioned tables");
-      return DJ_ERR_WORKSPACE;
-    }
+    prow[t]  = (Row*)(wsb + my.prow[t]);
+    d_cnt[t] = (int64_t*)(wsb + my.dcnt[t]);
     PassDesc desc{sub_bits ? 2 : 0, kNvlinkSeed, DJ_HASH_MURMUR3, 0, nbk, 1, 1, kAlignRows, nparts, sub_bits};
     PassBuffers pb{};
     pb.in_key = in_key[t]; pb.in_pay[0] = in_pay[t]; pb.out_rows = prow[t];
-    pb.nrows = n_in[t]; pb.d_child_off = d_off[t]; pb.d_child_cnt = d_cnt[t];
-    rc = run_partition_pass(desc, pb, pws, pw, st);
+    pb.nrows = n_in[t]; pb.d_child_off = (int64_t*)(wsb + my.doff[t]); pb.d_child_cnt = d_cnt[t];
+    rc = pass_histogram(desc, pb, wsb + my.pws[t], pw, st, &pstate[t]);
+    if (rc) return rc;
+  }
+  DJ_CUDA_TRY(cudaEventRecord(comm->ev_hist, st));
+  trace.mark("histograms done", st);
+  for (int t = 0; t < 2; t++) {
+    rc = pass_scatter(pstate[t], st);
     if (rc) return rc;
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_part[t], st));
     trace.mark(t ? "partition(R) done" : "partition(L) done", st);
-    trace.host(t ? "partition(R) launched" : "partition(L) launched");
+  }
+  trace.host("partition launched");
+
+  // ---- 2. sizes (communicate_sizes, src/all_to_all_comm.cpp:54-111): one all-gather of both
+  //         tables' bucket counts, as soon as the histograms are done
+  std::vector<int64_t> allc((size_t)world * 2 * nbk);
+  DJ_CUDA_TRY(cudaStreamWaitEvent(comm->ctrl_stream, comm->ev_hist, 0));
+  if (comm->peer_ok && 2 * nbk <= kInbox) {
+    // device -> every peer's inbox, straight from the histogram's output: no SM, no host hop
+    rc = peer_allgather(comm, d_cnt[0], 2 * nbk, allc.data());
+    if (rc) return rc;
+  } else {
+    int64_t* hp = comm->h_pinned + (256 << 10);  // D2H landing zone
+    DJ_CUDA_TRY(cudaMemcpyAsync(hp, d_cnt[0], (size_t)2 * nbk * 8, cudaMemcpyDeviceToHost, comm->ctrl_stream));
+    DJ_CUDA_TRY(cudaStreamSynchronize(comm->ctrl_stream));
+    rc = ctrl_allgather(comm, hp, 2 * nbk, allc.data());
+    if (rc) return rc;
+  }
+  trace.host("counts gathered");
+  if (timing) {
+    DJ_CUDA_TRY(cudaEventSynchronize(comm->ev_part[1]));
+    opts->t_partition_ms = ms_since(t0);
+    printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
+  }
+  auto tcomm = std::chrono::high_resolution_clock::now();
+
+  // rows of source `src`'s table t in sub-bucket `sub` of destination bucket q
+  auto cnt = [&](int src, int t, int q, int sub) {
+    return allc[((size_t)src * 2 + t) * nbk + ((size_t)q << sub_bits) + sub];
+  };
+  auto sent = [&](int src, int t, int q) {  // rows source `src` sends for destination bucket q
+    int64_t c = 0;
+    for (int sub = 0; sub < F1s; sub++) c += cnt(src, t, q, sub);
+    return c;
+  };
+  // where source s's rows start inside destination rank r's piece (batch b, table t), and its span
+  auto piece_begin = [&](int r, int b, int t, int s) {
+    int64_t at = 0;
+    for (int s2 = 0; s2 < s; s2++) at += pad_rows(sent(s2, t, b * G + r));
+    return at;
+  };
+  // my own send offsets: the aligned_offsets_kernel arithmetic restated on the host
+  std::vector<int64_t> send_begin((size_t)2 * nparts);
+  for (int t = 0; t < 2; t++) {
+    int64_t at = 0;
+    for (int q = 0; q < nparts; q++) {
+      send_begin[(size_t)t * nparts + q] = at;
+      at += pad_rows(sent(rank, t, q));
+    }
   }
 
-  // ---- 2-4. table by table: sizes (communicate_sizes, on the control communicator), receive
-  //           layout (allocate_communicated_table), exchange.  The left table's exchange starts
-  //           while the right table is still being partitioned; an event per (batch, table) hands
-  //           each received piece to the compute stream, so radix passes overlap later exchanges.
+  // ---- 3. receive layout of every rank (allocate_communicated_table) + the fit verdict, locally
+  std::vector<WsLayout> lay(world);
+  std::vector<int64_t> spans((size_t)odf * 2);
+  for (int r = 0; r < world; r++) {
+    for (int b = 0; b < odf; b++)
+      for (int t = 0; t < 2; t++) spans[(size_t)b * 2 + t] = piece_begin(r, b, t, G);
+    lay[r] = lay_out(H(r, 0), H(r, 1), spans.data());
+  }
+  for (int r = 0; r < world; r++)
+    if (lay[r].need > (size_t)H(r, 2)) {
+      if (opts) opts->workspace_needed = (int64_t)lay[rank].need;
+      set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
+                "(needs %zu of %lld bytes; this rank needs %zu)", r, lay[r].need, (long long)H(r, 2), lay[rank].need);
+      // nothing has been pushed yet and every rank takes this branch: just drain our own kernels
+      cudaStreamSynchronize(st);
+      return DJ_ERR_WORKSPACE;
+    }
   struct Piece {
     std::vector<int64_t> begin, count;  // per source
     int64_t span = 0, rows = 0;
@@ -617,53 +907,69 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     int* d_seg_parent = nullptr;
   };
   std::vector<Piece> pieces((size_t)odf * 2);
-  std::vector<int64_t> off[2], cntv[2], allc[2];
-  int64_t* hp   = comm->h_pinned + (256 << 10);  // D2H landing zone for offsets / counts
   int64_t* hseg = comm->h_pinned + (320 << 10);  // pinned staging for the segment tables
   DJ_REQUIRE(pieces.size() * 3 * (size_t)nseg <= (192u << 10), "distributed_inner_join: too many segments");
-  int64_t max_span[2] = {0, 0};
-  bool exchange_in_flight = false;
-  auto tcomm = std::chrono::high_resolution_clock::now();
+  for (int t = 0; t < 2; t++)
+    for (int b = 0; b < odf; b++) {
+      const size_t i = (size_t)b * 2 + t;
+      Piece& pc      = pieces[i];
+      pc.begin.resize(G);
+      pc.count.resize(G);
+      pc.data         = (Row*)(wsb + lay[rank].piece[i]);
+      pc.d_seg_begin  = (int64_t*)(wsb + lay[rank].seg_begin[i]);
+      pc.d_seg_end    = (int64_t*)(wsb + lay[rank].seg_end[i]);
+      pc.d_seg_parent = (int*)(wsb + lay[rank].seg_parent[i]);
+      int64_t* hb = hseg + i * 3 * nseg;
+      int* hpar   = reinterpret_cast<int*>(hb + 2 * (size_t)nseg);
+      for (int s = 0; s < G; s++) {
+        pc.begin[s] = pc.span;
+        pc.count[s] = sent(s, t, b * G + rank);
+        int64_t at  = pc.span;
+        for (int sub = 0; sub < F1s; sub++) {
+          const int64_t c          = cnt(s, t, b * G + rank, sub);
+          hb[s * F1s + sub]        = at;
+          hb[nseg + s * F1s + sub] = at + c;
+          hpar[s * F1s + sub]      = sub;
+          at += c;
+        }
+        pc.span += pad_rows(pc.count[s]);
+        pc.rows += pc.count[s];
+      }
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_begin, hb, (size_t)nseg * 8, cudaMemcpyHostToDevice, comm->ctrl_stream));
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_end, hb + nseg, (size_t)nseg * 8, cudaMemcpyHostToDevice, comm->ctrl_stream));
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_parent, hpar, (size_t)nseg * 4, cudaMemcpyHostToDevice, comm->ctrl_stream));
+    }
+  DJ_CUDA_TRY(cudaEventRecord(comm->ev_seg[0], comm->ctrl_stream));
+  trace.host("pieces laid out");
 
-  // rows of source `src`'s table t in sub-bucket `sub` of destination bucket q
-  auto cnt = [&](int src, int t, int q, int sub) {
-    return allc[t][(size_t)src * nbk + ((size_t)q << sub_bits) + sub];
-  };
+  // ---- 4. exchange (src/all_to_all_comm.cpp:126-189): every (batch, table) bucket run goes straight
+  //         from the partitioned table into the destination's receive piece
+  bool exchange_in_flight = false;
+  const bool measure      = opts && opts->measure_exchange && use_peer;
   auto issue_exchange = [&](int b, int t) -> int {
     Piece& pc = pieces[(size_t)b * 2 + t];
-    auto send_begin = [&](int dest) { return off[t][((size_t)b * G + dest) << sub_bits]; };
-    auto send_count = [&](int dest) {
-      int64_t c = 0;
-      for (int sub = 0; sub < F1s; sub++) c += cntv[t][(((size_t)b * G + dest) << sub_bits) + sub];
-      return c;
-    };
+    auto sbeg = [&](int dest) { return send_begin[(size_t)t * nparts + (size_t)b * G + dest]; };
     trace.mark(t ? "exchange(R) begin" : "exchange(L) begin", comm->comm_stream);
     // own bucket: device copy (src/all_to_all_comm.cpp:610-653); the rest over NVLink
     if (pc.count[rank] > 0)
-      DJ_CUDA_TRY(cudaMemcpyAsync(pc.data + pc.begin[rank], prow[t] + send_begin(rank),
+      DJ_CUDA_TRY(cudaMemcpyAsync(pc.data + pc.begin[rank], prow[t] + sbeg(rank),
                                   (size_t)pc.count[rank] * sizeof(Row), cudaMemcpyDeviceToDevice, comm->comm_stream));
     if (use_peer) {
       // push every peer's bucket into ITS receive piece with the copy engines (no SMs, so the
       // radix passes running meanwhile keep the whole GPU), then raise that peer's flag
-      const int slot = (b * 2 + t) % kFlagSlots;
+      const int slot = b * 2 + t;
       for (int i = 0; i < G; i++) {
         if (i == rank) continue;
         cudaStream_t ps = comm->peer_stream[i];
         DJ_CUDA_TRY(cudaStreamWaitEvent(ps, comm->ev_part[t], 0));
-        const int64_t ns = send_count(i);
+        if (measure && b == 0) DJ_CUDA_TRY(cudaEventRecord(comm->ev_xbeg[(size_t)t * G + i], ps));
+        const int64_t ns = sent(rank, t, b * G + i);
         if (ns > 0) {
-          // where my rows start inside peer i's piece: padded counts of the sources before me
-          int64_t dst_begin = 0;
-          for (int s2 = 0; s2 < rank; s2++) {
-            int64_t c = 0;
-            for (int sub = 0; sub < F1s; sub++) c += cnt(s2, t, b * G + i, sub);
-            dst_begin += pad_rows(c);
-          }
-          const int64_t* po = &peer_piece_off[(((size_t)t * world + i) * odf + b) * 2];
-          DJ_CUDA_TRY(cudaMemcpyAsync(peer_ws[i] + po[0] + dst_begin * sizeof(Row), prow[t] + send_begin(i),
-                                      (size_t)ns * sizeof(Row), cudaMemcpyDefault, ps));
-          if (opts) opts->bytes_sent += 16 * ns;
+          char* dst = peer_ws[i] + lay[i].piece[(size_t)b * 2 + t] + (size_t)piece_begin(i, b, t, rank) * sizeof(Row);
+          DJ_CUDA_TRY(cudaMemcpyAsync(dst, prow[t] + sbeg(i), (size_t)ns * sizeof(Row), cudaMemcpyDefault, ps));
+          if (opts) opts->bytes_sent += (int64_t)sizeof(Row) * ns;
         }
+        if (measure && b == odf - 1) DJ_CUDA_TRY(cudaEventRecord(comm->ev_xend[(size_t)t * G + i], ps));
         uint32_t* flag = comm->peer_flags[i] + (size_t)rank * kFlagSlots + slot;
         if (!comm->flag_by_memcpy &&
             comm->fn_write32((CUstream)ps, (CUdeviceptr)flag, seq, 0) != CUDA_SUCCESS)
@@ -682,16 +988,14 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     DJ_NCCL_TRY(ncclGroupStart());
     for (int i = 0; i < G; i++) {
       if (i == rank) continue;
-      const int64_t ns = send_count(i), nr = pc.count[i];
+      const int64_t ns = sent(rank, t, b * G + i), nr = pc.count[i];
       if (ns > 0) {
-        DJ_NCCL_TRY(ncclSend(prow[t] + send_begin(i), (size_t)ns * sizeof(Row), ncclInt8, i, comm->nccl,
-                             comm->comm_stream));
-        if (opts) opts->bytes_sent += 16 * ns;
+        DJ_NCCL_TRY(ncclSend(prow[t] + sbeg(i), (size_t)ns * sizeof(Row), ncclInt8, i, comm->nccl, comm->comm_stream));
+        if (opts) opts->bytes_sent += (int64_t)sizeof(Row) * ns;
       }
-      if (nr > 0) {
+      if (nr > 0)
         DJ_NCCL_TRY(ncclRecv(pc.data + pc.begin[i], (size_t)nr * sizeof(Row), ncclInt8, i, comm->nccl,
                              comm->comm_stream));
-      }
     }
     DJ_NCCL_TRY(ncclGroupEnd());
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[(size_t)b * 2 + t], comm->comm_stream));
@@ -706,168 +1010,84 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       for (int i = 0; i < G; i++)
         if (i != rank) cudaStreamSynchronize(comm->peer_stream[i]);
   };
-  for (int t = 0; t < 2; t++) {
-    // sizes of table t: wait only for ITS partition pass
-    DJ_CUDA_TRY(cudaStreamWaitEvent(comm->ctrl_stream, comm->ev_part[t], 0));
-    DJ_CUDA_TRY(cudaMemcpyAsync(hp, d_off[t], (size_t)(nbk + 1) * 8, cudaMemcpyDeviceToHost, comm->ctrl_stream));
-    DJ_CUDA_TRY(cudaMemcpyAsync(hp + nbk + 1, d_cnt[t], (size_t)nbk * 8, cudaMemcpyDeviceToHost, comm->ctrl_stream));
-    DJ_CUDA_TRY(cudaStreamSynchronize(comm->ctrl_stream));
-    off[t].assign(hp, hp + nbk + 1);
-    cntv[t].assign(hp + nbk + 1, hp + nbk + 1 + nbk);
-    if (timing && t == 1) {
-      opts->t_partition_ms = ms_since(t0);
-      printf("Rank %d: Hash partition takes %.0fms\n", rank, opts->t_partition_ms);
-      tcomm = std::chrono::high_resolution_clock::now();
-    }
-    trace.host(t ? "offsets(R) on host" : "offsets(L) on host");
-    allc[t].resize((size_t)world * nbk);
-    rc = ctrl_allgather(comm, cntv[t].data(), nbk, allc[t].data());
+  if (measure) {
+    rc = ensure_xevents(comm, 2 * G);
     if (rc) return rc;
-    trace.host(t ? "counts(R) gathered" : "counts(L) gathered");
-
-    // receive layout: per (batch) one padded piece per source, holding that source's F1s
-    // sub-buckets back to back
-    size_t need = arena.used;
-    for (int b = 0; b < odf; b++) {
-      Piece& pc = pieces[(size_t)b * 2 + t];
-      pc.begin.resize(G);
-      pc.count.resize(G);
-      for (int s = 0; s < G; s++) {
-        int64_t c = 0;
-        for (int sub = 0; sub < F1s; sub++) c += cnt(s, t, b * G + rank, sub);
-        pc.begin[s] = pc.span;
-        pc.count[s] = c;
-        pc.span += pad_rows(c);
-        pc.rows += c;
-      }
-      need += align_up((size_t)pc.span * sizeof(Row) + 128, 256) + 3 * align_up((size_t)nseg * 8, 256) + 1024;
-      max_span[t] = std::max(max_span[t], pc.span);
-    }
-    if (t == 1) need += side_ws_bytes(max_span[0], plan, nseg) + side_ws_bytes(max_span[1], plan, nseg) + 4096;
-    // pieces are laid out first (pure arithmetic), then ONE collective carries both the
-    // "it fits" verdict and the piece offsets the peers need for their pushes
-    const bool fits = need <= workspace_bytes;
-    for (int b = 0; b < odf && fits; b++) {
-      const size_t i  = (size_t)b * 2 + t;
-      Piece& pc       = pieces[i];
-      pc.data         = arena.take<Row>((size_t)pc.span + 8);
-      pc.d_seg_begin  = arena.take<int64_t>((size_t)nseg);
-      pc.d_seg_end    = arena.take<int64_t>((size_t)nseg);
-      pc.d_seg_parent = arena.take<int>((size_t)nseg);
-    }
-    {
-      std::vector<int64_t> mine_off((size_t)odf * 2 + 1), all_off((size_t)world * (odf * 2 + 1));
-      bool ok_local = fits;
-      for (int b = 0; b < odf && fits; b++) {
-        Piece& pc = pieces[(size_t)b * 2 + t];
-        if (!pc.data || !pc.d_seg_begin || !pc.d_seg_end || !pc.d_seg_parent) ok_local = false;
-      }
-      mine_off[0] = ok_local ? 1 : 0;
-      for (int b = 0; b < odf && ok_local; b++) {
-        mine_off[1 + (size_t)b * 2]     = (char*)pieces[(size_t)b * 2 + t].data - (char*)d_workspace;
-        mine_off[1 + (size_t)b * 2 + 1] = 0;
-      }
-      rc = ctrl_allgather(comm, mine_off.data(), odf * 2 + 1, all_off.data());
-      if (rc) return rc;
-      for (int r = 0; r < world; r++) {
-        if (!all_off[(size_t)r * (odf * 2 + 1)]) {
-          drain_exchange();
-          set_error("distributed_inner_join: workspace too small on rank %d for its received partitions "
-                    "(this rank needs %zu of %zu bytes)", r, need, workspace_bytes);
-          return DJ_ERR_WORKSPACE;
-        }
-        for (int k = 0; k < odf * 2; k++)
-          peer_piece_off[((size_t)t * world + r) * odf * 2 + k] = all_off[(size_t)r * (odf * 2 + 1) + 1 + k];
-      }
-    }
-    for (int b = 0; b < odf; b++) {
-      const size_t i = (size_t)b * 2 + t;
-      Piece& pc      = pieces[i];
-      int64_t* hb = hseg + i * 3 * nseg;
-      int* hpar   = reinterpret_cast<int*>(hb + 2 * (size_t)nseg);
-      for (int s = 0; s < G; s++) {
-        int64_t at = pc.begin[s];
-        for (int sub = 0; sub < F1s; sub++) {
-          const int64_t c          = cnt(s, t, b * G + rank, sub);
-          hb[s * F1s + sub]        = at;
-          hb[nseg + s * F1s + sub] = at + c;
-          hpar[s * F1s + sub]      = sub;
-          at += c;
-        }
-      }
-      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_begin, hb, (size_t)nseg * 8, cudaMemcpyHostToDevice, comm->ctrl_stream));
-      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_end, hb + nseg, (size_t)nseg * 8, cudaMemcpyHostToDevice, comm->ctrl_stream));
-      DJ_CUDA_TRY(cudaMemcpyAsync(pc.d_seg_parent, hpar, (size_t)nseg * 4, cudaMemcpyHostToDevice, comm->ctrl_stream));
-    }
-    DJ_CUDA_TRY(cudaEventRecord(comm->ev_seg[t], comm->ctrl_stream));
-
-    // exchanges in batch order (b,L),(b,R); what can start now: (0,L) after the left table's
-    // sizes, everything else once the right table's sizes are known
-    trace.host(t ? "pieces(R) laid out" : "pieces(L) laid out");
-    DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_part[t], 0));
-    if (t == 0) {
-      rc = issue_exchange(0, 0);
-      if (rc) return rc;
-    } else {
-      rc = issue_exchange(0, 1);
-      if (rc) return rc;
-      for (int b = 1; b < odf; b++)
-        for (int tt = 0; tt < 2; tt++) {
-          rc = issue_exchange(b, tt);
-          if (rc) return rc;
-        }
-    }
   }
+  // batch order (0,L),(0,R),(1,L),...: the left table's pushes start while the right table is
+  // still being partitioned
+  for (int b = 0; b < odf; b++)
+    for (int t = 0; t < 2; t++) {
+      if (b == 0) DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_part[t], 0));
+      rc = issue_exchange(b, t);
+      if (rc) return rc;
+    }
   if (timing) {
     DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
+    if (use_peer)
+      for (int i = 0; i < G; i++)
+        if (i != rank) DJ_CUDA_TRY(cudaStreamSynchronize(comm->peer_stream[i]));
     opts->t_comm_ms = ms_since(tcomm);
     for (int b = 0; b < odf; b++)
       printf("Rank %d: All-to-all communication on batch %d takes %.0fms\n", rank, b, opts->t_comm_ms / odf);
   }
   trace.host("exchanges issued");
   DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_seg[0], 0));
-  DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_seg[1], 0));
 
+  // ---- 5. local join per batch (src/distributed_join.cpp:283-322), appending into one output
+  arena.used             = lay[rank].join_mark;
   const size_t join_mark = arena.used;
   for (int b = 0; b < odf; b++) {
     auto tj    = std::chrono::high_resolution_clock::now();
     Piece& L   = pieces[(size_t)b * 2];
     Piece& R   = pieces[(size_t)b * 2 + 1];
     arena.used = join_mark;  // join scratch is reused batch after batch (same stream)
-    if (L.rows == 0 || R.rows == 0) continue;  // src/distributed_join.cpp:76-82
-    const bool swap = R.rows < L.rows;         // build on the smaller side
+    auto await_piece = [&](int t) -> int {
+      DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_batch[(size_t)b * 2 + t], 0));
+      if (use_peer) {
+        const int slot = b * 2 + t;
+        for (int src = 0; src < G; src++) {
+          if (src == rank) continue;
+          int r2 = stream_wait_flag(comm, st, comm->d_flags + (size_t)src * kFlagSlots + slot, seq);
+          if (r2) return r2;
+        }
+        trace.mark(t ? "arrived(R)" : "arrived(L)", st);
+      }
+      return DJ_OK;
+    };
+    if (L.rows == 0 || R.rows == 0) {  // src/distributed_join.cpp:76-82 (arrivals are still awaited)
+      for (int t = 0; t < 2; t++)
+        if ((rc = await_piece(t))) {
+          drain_exchange();
+          return rc;
+        }
+      continue;
+    }
+    const bool swap = build_on_right(L.rows, R.rows);
     PreparedSide side[2];
     for (int t = 0; t < 2; t++) {
       Piece& pc = t ? R : L;
-      DJ_CUDA_TRY(cudaStreamWaitEvent(st, comm->ev_batch[(size_t)b * 2 + t], 0));
-      if (use_peer) {
-        const int slot = (b * 2 + t) % kFlagSlots;
-        for (int src = 0; src < G; src++) {
-          if (src == rank) continue;
-          const CUdeviceptr fa = (CUdeviceptr)(comm->d_flags + (size_t)src * kFlagSlots + slot);
-          CUresult wr = CUDA_ERROR_NOT_SUPPORTED;
-          if (comm->wait_flush) {
-            wr = comm->fn_wait32((CUstream)st, fa, seq, CU_STREAM_WAIT_VALUE_GEQ | CU_STREAM_WAIT_VALUE_FLUSH);
-            if (wr != CUDA_SUCCESS) comm->wait_flush = false;
-          }
-          if (wr != CUDA_SUCCESS) wr = comm->fn_wait32((CUstream)st, fa, seq, CU_STREAM_WAIT_VALUE_GEQ);
-          if (wr != CUDA_SUCCESS) {
-            drain_exchange();
-            set_error("distributed_inner_join: cuStreamWaitValue32 failed with CUresult %d", (int)wr);
-            return DJ_ERR_CUDA;
-          }
-        }
-        trace.mark(t ? "arrived(R)" : "arrived(L)", st);
+      // each piece is awaited right before ITS radix pass: the left table's pass overlaps the
+      // right table's exchange
+      if ((rc = await_piece(t))) {
+        drain_exchange();
+        return rc;
       }
       TableInput in{nullptr, nullptr, pc.data, pc.span, pc.d_seg_begin, pc.d_seg_end, nseg, pc.d_seg_parent,
                     sub_bits > 0};
       trace.mark(t ? "radix(R) begin" : "radix(L) begin", st);
       rc = prepare_side(in, plan, &side[t], arena, st);
-      if (rc) return rc;
+      if (rc) {
+        drain_exchange();
+        return rc;
+      }
       trace.mark(t ? "radix(R) end" : "radix(L) end", st);
     }
     rc = join_prepared(side[swap ? 1 : 0], side[swap ? 0 : 1], plan, out, out_capacity, d_count, swap, st);
-    if (rc) return rc;
+    if (rc) {
+      drain_exchange();
+      return rc;
+    }
     trace.mark("join end", st);
     if (timing) {
       DJ_CUDA_TRY(cudaStreamSynchronize(st));
@@ -877,28 +1097,72 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     }
   }
   trace.host("join launched");
-  DJ_CUDA_TRY(cudaMemcpyAsync(comm->h_pinned, d_count, 8, cudaMemcpyDeviceToHost, st));
+
+  // ---- 6. the overflow verdict is collective (every rank returns DJ_ERR_OVERFLOW if any rank's
+  //         output did not fit, so that callers can retry together) and costs no collective: a
+  //         one-thread kernel stores this rank's verdict into every peer's flag block over NVLink,
+  //         the stream waits for the peers' words, and ONE synchronisation returns count + verdicts.
+  int64_t* h_res = comm->h_pinned + (128 << 10);
+  if (use_peer) {
+    trace.mark("verdict begin", st);
+    verdict_kernel<<<1, 32, 0, st>>>((const unsigned long long*)d_count, (unsigned long long)out_capacity,
+                                     comm->d_peer_flags, world, rank, kFlagSlots, kFlagSlots - 1, seq);
+    DJ_LAUNCH_CHECK();
+    for (int src = 0; src < G; src++) {
+      if (src == rank) continue;
+      rc = stream_wait_flag(comm, st, comm->d_flags + (size_t)src * kFlagSlots + (kFlagSlots - 1), seq << 1);
+      if (rc) {
+        drain_exchange();
+        return rc;
+      }
+    }
+    trace.mark("verdicts received", st);
+    DJ_CUDA_TRY(cudaMemcpy2DAsync(h_res + 1, 4, comm->d_flags + (kFlagSlots - 1), (size_t)kFlagSlots * 4, 4, world,
+                                  cudaMemcpyDeviceToHost, st));
+  }
+  DJ_CUDA_TRY(cudaMemcpyAsync(h_res, d_count, 8, cudaMemcpyDeviceToHost, st));
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  trace.host("main stream drained");
   DJ_CUDA_TRY(cudaStreamSynchronize(comm->comm_stream));
   trace.host("streams drained");
   if (use_peer)
     for (int i = 0; i < G; i++)
       if (i != rank) DJ_CUDA_TRY(cudaStreamSynchronize(comm->peer_stream[i]));  // my buckets may be reused now
-  *h_out_count = comm->h_pinned[0];
+  *h_out_count = h_res[0];
+  if (measure) {
+    // per-direction NVLink throughput of this rank's pushes: from "partition of table t done" to
+    // the last push of table t complete, per peer stream; the slowest stream bounds the table
+    for (int t = 0; t < 2; t++) {
+      float worst = 0;
+      for (int i = 0; i < G; i++) {
+        if (i == rank) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, comm->ev_xbeg[(size_t)t * G + i], comm->ev_xend[(size_t)t * G + i]) == cudaSuccess)
+          worst = std::max(worst, ms);
+      }
+      opts->t_exchange_ms[t] = worst;
+    }
+    cudaGetLastError();
+  }
   trace.dump(rank);
-  // the overflow verdict is collective: every rank returns DJ_ERR_OVERFLOW if any rank's
-  // output did not fit, so that callers can retry together
-  {
+  int over_rank = -1;
+  if (use_peer) {
+    const uint32_t* hv = reinterpret_cast<const uint32_t*>(h_res + 1);
+    for (int r = 0; r < world; r++)
+      if (r != rank && (hv[r] & 1u)) over_rank = r;
+    if (*h_out_count > out_capacity) over_rank = rank;
+  } else {
     int64_t over = *h_out_count > out_capacity ? 1 : 0;
     std::vector<int64_t> overs(world);
     rc = ctrl_allgather(comm, &over, 1, overs.data());
     if (rc) return rc;
     for (int r = 0; r < world; r++)
-      if (overs[r]) {
-        set_error("join output does not fit on rank %d (this rank: %lld rows, capacity %lld)", r,
-                  (long long)*h_out_count, (long long)out_capacity);
-        return DJ_ERR_OVERFLOW;
-      }
+      if (overs[r]) over_rank = r;
+  }
+  if (over_rank >= 0) {
+    set_error("join output does not fit on rank %d (this rank: %lld rows, capacity %lld)", over_rank,
+              (long long)*h_out_count, (long long)out_capacity);
+    return DJ_ERR_OVERFLOW;
   }
   return DJ_OK;
 }

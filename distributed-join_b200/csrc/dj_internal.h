@@ -63,6 +63,41 @@ struct PassBuffers {
   int64_t* d_child_cnt       = nullptr;  // [P*F] out (aligned passes): rows per child bucket
 };
 
+// Device-side view of one pass (kernel argument).
+struct PassDev {
+  const int64_t* in_key;
+  const int64_t* in_pay[kMaxPayload];
+  int64_t* out_key;
+  int64_t* out_pay[kMaxPayload];
+  const Row* in_rows;        // row-format input (nullptr: SoA in_key / in_pay[0])
+  Row* out_rows;             // row-format output (scatter_rows_kernel)
+  int64_t in_total;          // rows in the input arrays (TMA windows are clamped to the column end)
+  const int64_t* seg_begin;  // [S] first row of every input segment
+  const int64_t* seg_end;    // [S] one past its last row
+  const int* seg_parent;     // [S] output parent bucket the segment's rows belong to
+  unsigned long long* counts;  // [P*F+1]
+  unsigned long long* cursor;  // [P*F]
+  const int* hist_tiles;       // [S+1] prefix of hist tiles per segment
+  const int* scat_tiles;       // [S+1] prefix of scatter tiles per segment
+  int S, P, F;
+  uint32_t seed;
+  int hash_id, shift, pow2;
+  int nparts, sub_bits;  // mode 2: bucket = (row_hash % nparts) << sub_bits | top sub_bits of local_hash
+};
+
+// A pass runs in two stream-ordered halves so that callers can put work between them: the
+// distributed join all-gathers the histogram's counts while the scatter kernels already run.
+//   pass_histogram  tile plan + key histogram + child offsets (+ cursors)
+//   pass_scatter    the scatter kernel
+struct PassState {
+  PassDev dev;
+  int mode, npay;
+  int64_t span;
+};
+int pass_histogram(const PassDesc& desc, const PassBuffers& buf, void* d_ws, size_t ws_bytes,
+                   cudaStream_t stream, PassState* state);
+int pass_scatter(const PassState& state, cudaStream_t stream);
+
 size_t pass_workspace_bytes(int P, int F, int nseg = 0);
 int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws, size_t ws_bytes,
                        cudaStream_t stream);

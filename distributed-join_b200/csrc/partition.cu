@@ -38,26 +38,6 @@ constexpr int kScatterThreads = 512;
 constexpr int kRowsPerThread  = 8;
 constexpr int kScatterTile    = kScatterThreads * kRowsPerThread;  // 4096 rows
 
-struct PassDev {
-  const int64_t* in_key;
-  const int64_t* in_pay[kMaxPayload];
-  int64_t* out_key;
-  int64_t* out_pay[kMaxPayload];
-  const Row* in_rows;        // row-format input (nullptr: SoA in_key / in_pay[0])
-  Row* out_rows;             // row-format output (scatter_rows_kernel)
-  int64_t in_total;          // rows in the input arrays (TMA windows are clamped to the column end)
-  const int64_t* seg_begin;  // [S] first row of every input segment
-  const int64_t* seg_end;    // [S] one past its last row
-  const int* seg_parent;     // [S] output parent bucket the segment's rows belong to
-  unsigned long long* counts;  // [P*F+1]
-  unsigned long long* cursor;  // [P*F]
-  const int* hist_tiles;       // [S+1] prefix of hist tiles per segment
-  const int* scat_tiles;       // [S+1] prefix of scatter tiles per segment
-  int S, P, F;
-  uint32_t seed;
-  int hash_id, shift, pow2;
-  int nparts, sub_bits;  // mode 2: bucket = (row_hash % nparts) << sub_bits | top sub_bits of local_hash
-};
 
 template <int MODE>
 __device__ __forceinline__ int bucket_of(int64_t key, const PassDev& d)
@@ -825,8 +805,8 @@ size_t pass_workspace_bytes(int P, int F, int nseg)
   return total + 1024;
 }
 
-int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws, size_t ws_bytes,
-                       cudaStream_t stream)
+int pass_histogram(const PassDesc& desc, const PassBuffers& buf, void* d_ws, size_t ws_bytes,
+                   cudaStream_t stream, PassState* state)
 {
   DJ_REQUIRE(desc.F >= 1 && desc.F <= kMaxFanout, "partition: fan-out %d out of range", desc.F);
   DJ_REQUIRE(desc.P >= 1 && desc.P <= kMaxFanout, "partition: parent count %d out of range", desc.P);
@@ -857,8 +837,6 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
   }
 
   DJ_CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 1) * 8, stream));
-  // 32-bit destination offsets in the SoA TMA kernel: input rows + worst-case padding must fit
-  const int64_t span = buf.nrows + (int64_t)nb * desc.align_rows;
   plan_kernel<<<1, 1024, 0, stream>>>(buf.d_parent_off, buf.d_seg_begin, buf.d_seg_end, buf.d_seg_parent,
                                       buf.nrows, S, kScatterTile, seg_begin, seg_end, seg_parent, hist_tiles,
                                       scat_tiles);
@@ -918,10 +896,28 @@ int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws,
     }
     DJ_CUDA_TRY(cudaMemcpyAsync(cursor, buf.d_child_off, nb * 8, cudaMemcpyDeviceToDevice, stream));
   }
+  state->dev  = dev;
+  state->mode = desc.mode;
+  state->npay = desc.npay;
+  // 32-bit destination offsets in the SoA TMA kernel: input rows + worst-case padding must fit
+  state->span = buf.nrows + (int64_t)nb * desc.align_rows;
+  return DJ_OK;
+}
 
-  if (desc.mode == 0) return launch_scatter_npay<0>(dev, desc.npay, desc.F, span, stream);
-  if (desc.mode == 1) return launch_scatter_npay<1>(dev, desc.npay, desc.F, span, stream);
-  return launch_scatter_npay<2>(dev, desc.npay, desc.F, span, stream);
+int pass_scatter(const PassState& st, cudaStream_t stream)
+{
+  if (st.mode == 0) return launch_scatter_npay<0>(st.dev, st.npay, st.dev.F, st.span, stream);
+  if (st.mode == 1) return launch_scatter_npay<1>(st.dev, st.npay, st.dev.F, st.span, stream);
+  return launch_scatter_npay<2>(st.dev, st.npay, st.dev.F, st.span, stream);
+}
+
+int run_partition_pass(const PassDesc& desc, const PassBuffers& buf, void* d_ws, size_t ws_bytes,
+                       cudaStream_t stream)
+{
+  PassState st;
+  int rc = pass_histogram(desc, buf, d_ws, ws_bytes, stream, &st);
+  if (rc) return rc;
+  return pass_scatter(st, stream);
 }
 
 }  // namespace dj

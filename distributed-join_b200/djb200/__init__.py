@@ -23,6 +23,7 @@ SEED_IB = 87654321  # src/distributed_join.cpp:160
 DEFAULT_HASH_SEED = 0
 GEN_SEED = 1234  # generate_dataset/generate_dataset.cuh:44
 
+ERR_WORKSPACE = 3
 ERR_OVERFLOW = 5
 
 
@@ -50,6 +51,10 @@ class JoinOptions(C.Structure):
         ("t_comm_ms", C.c_double),
         ("t_join_ms", C.c_double),
         ("bytes_sent", C.c_int64),
+        ("workspace_needed", C.c_int64),
+        ("measure_exchange", C.c_int),
+        ("pad_", C.c_int),
+        ("t_exchange_ms", C.c_double * 2),
     ]
 
 
@@ -59,7 +64,8 @@ ABI_SYMBOLS = [
     "dj_partition_ids_i64",
     "dj_hash_partition_workspace_bytes", "dj_hash_partition_i64", "dj_inner_join_workspace_bytes",
     "dj_inner_join_i64", "dj_generate_build_bitmap", "dj_generate_rows_i64", "dj_multiset_checksum4",
-    "dj_comm_unique_id", "dj_comm_create", "dj_comm_destroy", "dj_comm_rank", "dj_comm_size",
+    "dj_comm_unique_id", "dj_comm_create", "dj_comm_destroy", "dj_comm_release_workspace", "dj_comm_rank",
+    "dj_comm_size",
     "dj_comm_allgather_i64", "dj_comm_barrier", "dj_all_to_all", "dj_comm_group_start",
     "dj_comm_group_end", "dj_comm_send", "dj_comm_recv", "dj_distributed_inner_join_workspace_bytes",
     "dj_distributed_inner_join_i64", "dj_distributed_inner_join_host_workspace_bytes",
@@ -98,6 +104,7 @@ def lib() -> C.CDLL:
     L.dj_comm_unique_id.argtypes = [vp]
     L.dj_comm_create.argtypes = [C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.dj_comm_destroy.argtypes = [vp]
+    L.dj_comm_release_workspace.argtypes = [vp]
     L.dj_comm_rank.argtypes = [vp]
     L.dj_comm_size.argtypes = [vp]
     L.dj_comm_allgather_i64.argtypes = [vp, C.POINTER(i64), C.c_int, C.POINTER(i64), vp]
@@ -300,6 +307,10 @@ class Comm:
     def barrier(self):
         _check(lib().dj_comm_barrier(self.handle, _stream()))
 
+    def release_workspace(self):
+        """Collective: close the peers' CUDA IPC mappings of join workspaces (call before freeing one)."""
+        _check(lib().dj_comm_release_workspace(self.handle))
+
     def destroy(self):
         if self.handle:
             lib().dj_comm_destroy(self.handle)
@@ -313,8 +324,10 @@ class JoinResult:
     options: JoinOptions
 
 
-def distributed_inner_join(comm, lk, lp, rk, rp, odf=1, capacity=None, ws=None, outs=None, report_timing=False):
-    """distributed_inner_join (src/distributed_join.cpp:134-340) on device tensors through the C ABI."""
+def distributed_inner_join(comm, lk, lp, rk, rp, odf=1, capacity=None, ws=None, outs=None, report_timing=False,
+                           measure_exchange=False):
+    """distributed_inner_join (src/distributed_join.cpp:134-340) on device tensors through the C ABI.
+    Both retry loops are collective: every rank receives DJ_ERR_OVERFLOW / DJ_ERR_WORKSPACE together."""
     lk, lp, rk, rp = map(_i64dev, (lk, lp, rk, rp))
     nl, nr = lk.numel(), rk.numel()
     world = comm.size if comm else 1
@@ -327,17 +340,26 @@ def distributed_inner_join(comm, lk, lp, rk, rp, odf=1, capacity=None, ws=None, 
         if outs is None or outs[0].numel() < capacity:
             outs = [torch.empty(capacity, dtype=torch.int64, device=dev) for _ in range(4)]
         cnt = C.c_int64(0)
-        opts = JoinOptions(odf, 1 if report_timing else 0, 0, 0, 0, 0)
+        opts = JoinOptions(odf, 1 if report_timing else 0)
+        opts.measure_exchange = 1 if measure_exchange else 0
         rc = _check(lib().dj_distributed_inner_join_i64(comm.handle if comm else None, _ptr(lk), _ptr(lp), nl,
                                                         _ptr(rk), _ptr(rp), nr, *[_ptr(o) for o in outs], capacity,
                                                         C.byref(cnt), C.byref(opts), _ptr(ws), ws.numel(), _stream()),
-                    allow=(ERR_OVERFLOW,))
+                    allow=(ERR_OVERFLOW, ERR_WORKSPACE) if world > 1 else (ERR_OVERFLOW,))
         n = cnt.value
         if rc == 0:
             return JoinResult(tuple(o[:n] for o in outs), n, opts)
+        if rc == ERR_WORKSPACE:
+            # a rank receives more rows than the balanced estimate (skewed slices / hot keys): peers unmap
+            # the old workspace, everybody grows to what the library asked for, and all retry
+            comm.release_workspace()
+            need = int(opts.workspace_needed)
+            ws = workspace(max(ws.numel(), need + need // 8), dev)
+            continue
         # every rank must retry together: agree on the largest need
         need = max(comm.allgather_i64([n])) if comm and comm.size > 1 else n
-        capacity, outs = need, None
+        capacity = need
+        outs = None
 
 
 def distributed_inner_join_host(comm, h_lk, h_lp, h_rk, h_rp, h_outs, odf=1, ws=None):

@@ -59,11 +59,23 @@ static std::unique_ptr<table> fused_join(cudf::table_view left, cudf::table_view
       if (p) cudaFree(p);
     }
   } ws;
-  if (ws.n < ws_bytes) {
-    if (ws.p) CUDA_RT_CALL(cudaFree(ws.p));
-    CUDA_RT_CALL(cudaMalloc(&ws.p, ws_bytes));
-    ws.n = ws_bytes;
-  }
+  // Growing is collective: peers hold CUDA IPC mappings of the old allocation, which must be closed
+  // before it is freed (dj_comm_release_workspace).  Every rank evaluates the same condition.
+  auto grow = [&](size_t want) {
+    vector<int64_t> wants(world);
+    int64_t mine = ws.n < want ? (int64_t)want : 0;
+    nccl->allgather_i64(&mine, 1, wants.data());
+    bool any = false;
+    for (int64_t w : wants) any = any || w > 0;
+    if (!any) return;
+    DJ_CALL(dj_comm_release_workspace(nccl->comm));
+    if (ws.n < want) {
+      if (ws.p) CUDA_RT_CALL(cudaFree(ws.p));
+      CUDA_RT_CALL(cudaMalloc(&ws.p, want));
+      ws.n = want;
+    }
+  };
+  grow(ws_bytes);
   // first guess for the output: as many rows as the larger input; retried collectively if short
   int64_t capacity = std::max<int64_t>(std::max(nl, nr), 1);
   for (;;) {
@@ -79,7 +91,13 @@ static std::unique_ptr<table> fused_join(cudf::table_view left, cudf::table_view
       right.column(0).head<int64_t>(), right.column(1).head<int64_t>(), nr,
       cols[0]->mutable_view().head<int64_t>(), cols[1]->mutable_view().head<int64_t>(),
       cols[2]->mutable_view().head<int64_t>(), cols[3]->mutable_view().head<int64_t>(), capacity, &n_out, &opts,
-      ws.data(), ws_bytes, nullptr);
+      ws.data(), ws.n, nullptr);
+    if (rc == DJ_ERR_WORKSPACE && world > 1) {
+      // skewed sizes: a rank receives more than the balanced estimate.  Every rank returned this
+      // code together; each grows to what it was told it needs (plus headroom) and all retry.
+      grow(opts.workspace_needed > 0 ? (size_t)(opts.workspace_needed + opts.workspace_needed / 8) : ws.n);
+      continue;
+    }
     if (rc == DJ_OK) {
       for (auto& c : cols) c->set_size((cudf::size_type)n_out);
       return std::make_unique<table>(std::move(cols));

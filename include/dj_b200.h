@@ -141,6 +141,9 @@ typedef struct dj_comm dj_comm_t;
 int dj_comm_unique_id(void* h_id128);
 int dj_comm_create(int rank, int size, const void* h_id128, dj_comm_t** out);
 int dj_comm_destroy(dj_comm_t* comm);
+/* Collective.  Closes every rank's CUDA IPC mappings of the peers' join workspaces; call it on all
+ * ranks before freeing or reallocating a workspace that a distributed join has used. */
+int dj_comm_release_workspace(dj_comm_t* comm);
 int dj_comm_rank(const dj_comm_t* comm);
 int dj_comm_size(const dj_comm_t* comm);
 
@@ -186,6 +189,12 @@ typedef struct {
   int report_timing;     /* print the reference's per-stage lines to stdout */
   double t_partition_ms, t_comm_ms, t_join_ms; /* filled when report_timing */
   int64_t bytes_sent;    /* bytes this rank sent over NVLink                 */
+  int64_t workspace_needed; /* out: with DJ_ERR_WORKSPACE, the bytes THIS rank needs (every rank
+                               returns the error together, so callers can grow and retry)      */
+  int measure_exchange;  /* in: time this rank's NVLink pushes with CUDA events                */
+  int pad_;
+  double t_exchange_ms[2]; /* out (measure_exchange): per table, from "partition done" to the
+                              last push complete on the slowest peer stream                    */
 } dj_join_options;
 
 size_t dj_distributed_inner_join_workspace_bytes(int64_t nleft, int64_t nright, int world,

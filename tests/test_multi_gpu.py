@@ -97,6 +97,17 @@ def main():
     def everything_empty_right(r, w):
         return np.arange(1000) + r, np.arange(1000), np.empty(0, np.int64), np.empty(0, np.int64)
 
+    def one_rank_holds_everything(r, w):
+        # rank 0 owns both tables entirely; the others hold nothing but RECEIVE 1/w of the rows: the
+        # balanced workspace estimate of the empty ranks is far too small -> collective grow-and-retry
+        if r != 0:
+            e = np.empty(0, np.int64)
+            return e, e, e, e
+        rng = np.random.default_rng(7)
+        return (rng.permutation(1_500_000), np.arange(1_500_000), rng.integers(0, 1_500_000, 2_000_000),
+                np.arange(2_000_000) + 10**9)
+
+    explicit_case("one rank holds everything (workspace regrow)", one_rank_holds_everything)
     explicit_case("empty left slice on rank 0", empty_on_rank0)
     explicit_case("tiny tables with duplicates", tiny_with_duplicates)
     explicit_case("uneven slices, duplicates on both sides", uneven_slices)
