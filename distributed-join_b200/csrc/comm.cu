@@ -1176,6 +1176,147 @@ extern "C" size_t dj_distributed_inner_join_host_workspace_bytes(int64_t nleft, 
          4 * align_up((size_t)out_capacity * 8, 256) + 8192;
 }
 
+// Single-GPU end-to-end join with HOST tables, streamed: the PCIe link is the bottleneck (25.6 GB in,
+// 7.7 GB out at 800M x 800M against ~50 ms of GPU work), so the call is organised around keeping
+// both directions of the link busy:
+//   1. the build table goes up first and is radix-partitioned while the probe table's first chunks
+//      are already on the wire;
+//   2. the probe table goes up in chunks (double-buffered); each chunk is partitioned with the same
+//      radix plan and joined against the resident build buckets as soon as it has landed -- the GPU
+//      re-inserts the build rows once per chunk, which costs HBM bandwidth that is idle anyway;
+//   3. each chunk's matches go down on their own stream while the next chunk comes up (full duplex).
+// What is left after the last byte has arrived is one chunk's join and one chunk's matches.
+static int host_join_streamed(const int64_t* h_left_key, const int64_t* h_left_payload, int64_t nleft,
+                              const int64_t* h_right_key, const int64_t* h_right_payload, int64_t nright,
+                              int64_t* const h_out[4], int64_t out_capacity, int64_t* h_out_count,
+                              dj_join_options* opts, void* d_workspace, size_t workspace_bytes, cudaStream_t st)
+{
+  *h_out_count = 0;
+  if (opts) {
+    opts->t_partition_ms = opts->t_comm_ms = opts->t_join_ms = 0;
+    opts->bytes_sent = opts->workspace_needed = 0;
+  }
+  if (nleft == 0 || nright == 0) return DJ_OK;  // src/distributed_join.cpp:76-82
+  const bool swap      = build_on_right(nleft, nright);
+  const int64_t nb     = swap ? nright : nleft, np = swap ? nleft : nright;
+  const int64_t* h_bk  = swap ? h_right_key : h_left_key;
+  const int64_t* h_bp  = swap ? h_right_payload : h_left_payload;
+  const int64_t* h_pk  = swap ? h_left_key : h_right_key;
+  const int64_t* h_pp  = swap ? h_left_payload : h_right_payload;
+  const RadixPlan plan = plan_for(nb, false);
+  int nchunks          = 16;
+  {
+    const char* e = getenv("DJ_HOST_CHUNKS");
+    if (e && atoi(e) > 0) nchunks = atoi(e);
+  }
+  int64_t chunk = (np + nchunks - 1) / nchunks;
+  if (chunk < (1 << 20)) chunk = std::min<int64_t>(np, 1 << 20);  // small tables: few chunks
+  chunk   = (chunk + 1) / 2 * 2;  // even row counts keep every chunk's host columns 16-byte aligned
+  nchunks = (int)((np + chunk - 1) / chunk);
+  int64_t* h_cnt = nullptr;  // pinned: running match count after every chunk (allocated before any work is queued)
+  DJ_CUDA_TRY(cudaMallocHost(&h_cnt, (size_t)(nchunks + 1) * 8));
+  struct PinGuard {
+    int64_t* p;
+    ~PinGuard() { cudaFreeHost(p); }
+  } pin_guard{h_cnt};
+
+  Arena arena(d_workspace, workspace_bytes);
+  int64_t* d_count = arena.take<int64_t>(32);
+  int64_t* dbk     = arena.take<int64_t>((size_t)nb);
+  int64_t* dbp     = arena.take<int64_t>((size_t)nb);
+  int64_t* dck[2], *dcp[2];
+  for (int i = 0; i < 2; i++) {  // one buffer is enough for a single chunk
+    dck[i] = (i == 0 || nchunks > 1) ? arena.take<int64_t>((size_t)chunk) : dck[0];
+    dcp[i] = (i == 0 || nchunks > 1) ? arena.take<int64_t>((size_t)chunk) : dcp[0];
+  }
+  int64_t* o[4];
+  for (int c = 0; c < 4; c++) o[c] = arena.take<int64_t>((size_t)out_capacity);
+  if (!d_count || !dbk || !dbp || !dck[1] || !dcp[1] || !o[3]) {
+    set_error("distributed_inner_join_host: workspace too small");
+    return DJ_ERR_WORKSPACE;
+  }
+  cudaStream_t up = nullptr, down = nullptr;
+  std::vector<cudaEvent_t> ev;  // [0] build up, then per chunk: landed, partitioned, joined
+  auto cleanup = [&]() {
+    for (auto e : ev) cudaEventDestroy(e);
+    if (up) cudaStreamDestroy(up);
+    if (down) cudaStreamDestroy(down);
+  };
+  struct Guard {
+    decltype(cleanup)& f;
+    ~Guard() { f(); }
+  } guard{cleanup};
+  DJ_CUDA_TRY(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+  DJ_CUDA_TRY(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+  ev.resize(2 + (size_t)nchunks * 3, nullptr);
+  for (auto& e : ev) DJ_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaEvent_t ev_start = ev[1];
+  auto ev_landed = [&](int c) { return ev[2 + (size_t)c * 3]; };
+  auto ev_parted = [&](int c) { return ev[3 + (size_t)c * 3]; };
+  auto ev_joined = [&](int c) { return ev[4 + (size_t)c * 3]; };
+
+  // the caller's stream orders the call: uploads start after whatever it had queued
+  DJ_CUDA_TRY(cudaEventRecord(ev_start, st));
+  DJ_CUDA_TRY(cudaStreamWaitEvent(up, ev_start, 0));
+  DJ_CUDA_TRY(cudaStreamWaitEvent(down, ev_start, 0));
+  DJ_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+  DJ_CUDA_TRY(cudaMemcpyAsync(dbk, h_bk, (size_t)nb * 8, cudaMemcpyHostToDevice, up));
+  DJ_CUDA_TRY(cudaMemcpyAsync(dbp, h_bp, (size_t)nb * 8, cudaMemcpyHostToDevice, up));
+  DJ_CUDA_TRY(cudaEventRecord(ev[0], up));
+
+  // build side: partitioned once, resident for the whole call
+  PreparedSide build{}, probe{};
+  DJ_CUDA_TRY(cudaStreamWaitEvent(st, ev[0], 0));
+  TableInput tb{dbk, dbp, nullptr, nb, nullptr, nullptr, 0};
+  int rc = prepare_side(tb, plan, &build, arena, st);
+  if (rc) return rc;
+  const size_t chunk_mark = arena.used;
+  int64_t* out4[4] = {o[0], o[1], o[2], o[3]};
+  int64_t done_rows = 0;  // output rows already on their way to the host
+  auto drain = [&](int c) -> int {  // chunk c's matches -> host, on the download stream
+    DJ_CUDA_TRY(cudaEventSynchronize(ev_joined(c)));
+    int64_t upto = h_cnt[c] < out_capacity ? h_cnt[c] : out_capacity;
+    if (upto > done_rows) {
+      DJ_CUDA_TRY(cudaStreamWaitEvent(down, ev_joined(c), 0));
+      for (int col = 0; col < 4; col++)
+        DJ_CUDA_TRY(cudaMemcpyAsync(h_out[col] + done_rows, o[col] + done_rows, (size_t)(upto - done_rows) * 8,
+                                    cudaMemcpyDeviceToHost, down));
+      done_rows = upto;
+    }
+    return DJ_OK;
+  };
+  for (int c = 0; c < nchunks; c++) {
+    const int64_t r0 = (int64_t)c * chunk, n = std::min(chunk, np - r0);
+    const int bi     = c & 1;
+    if (c >= 2) DJ_CUDA_TRY(cudaStreamWaitEvent(up, ev_parted(c - 2), 0));  // the buffer's previous chunk is consumed
+    DJ_CUDA_TRY(cudaMemcpyAsync(dck[bi], h_pk + r0, (size_t)n * 8, cudaMemcpyHostToDevice, up));
+    DJ_CUDA_TRY(cudaMemcpyAsync(dcp[bi], h_pp + r0, (size_t)n * 8, cudaMemcpyHostToDevice, up));
+    DJ_CUDA_TRY(cudaEventRecord(ev_landed(c), up));
+
+    DJ_CUDA_TRY(cudaStreamWaitEvent(st, ev_landed(c), 0));
+    arena.used = chunk_mark;  // probe scratch is reused chunk after chunk (same stream)
+    TableInput tp{dck[bi], dcp[bi], nullptr, n, nullptr, nullptr, 0};
+    rc = prepare_side(tp, plan, &probe, arena, st);
+    if (rc) return rc;
+    DJ_CUDA_TRY(cudaEventRecord(ev_parted(c), st));
+    rc = join_prepared(build, probe, plan, out4, out_capacity, d_count, swap, st);
+    if (rc) return rc;
+    DJ_CUDA_TRY(cudaMemcpyAsync(h_cnt + c, d_count, 8, cudaMemcpyDeviceToHost, st));
+    DJ_CUDA_TRY(cudaEventRecord(ev_joined(c), st));
+    // the previous chunk's matches go down while this chunk is being joined and the next comes up
+    if (c >= 1 && (rc = drain(c - 1))) return rc;
+  }
+  if ((rc = drain(nchunks - 1))) return rc;
+  DJ_CUDA_TRY(cudaStreamSynchronize(down));
+  DJ_CUDA_TRY(cudaStreamSynchronize(st));
+  *h_out_count = h_cnt[nchunks - 1];
+  if (*h_out_count > out_capacity) {
+    set_error("join output needs %lld rows, capacity %lld", (long long)*h_out_count, (long long)out_capacity);
+    return DJ_ERR_OVERFLOW;
+  }
+  return DJ_OK;
+}
+
 extern "C" int dj_distributed_inner_join_i64_host(
   dj_comm_t* comm, const int64_t* h_left_key, const int64_t* h_left_payload, int64_t nleft,
   const int64_t* h_right_key, const int64_t* h_right_payload, int64_t nright, int64_t* h_out_lk,
@@ -1183,8 +1324,12 @@ extern "C" int dj_distributed_inner_join_i64_host(
   int64_t* h_out_count, dj_join_options* opts, void* d_workspace, size_t workspace_bytes,
   void* stream)
 {
-  DJ_REQUIRE(d_workspace && h_out_count, "distributed_inner_join_host: bad argument");
+  DJ_REQUIRE(d_workspace && h_out_count && nleft >= 0 && nright >= 0, "distributed_inner_join_host: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  int64_t* h[4]   = {h_out_lk, h_out_lp, h_out_rk, h_out_rp};
+  if (!comm || comm->size == 1)
+    return host_join_streamed(h_left_key, h_left_payload, nleft, h_right_key, h_right_payload, nright, h,
+                              out_capacity, h_out_count, opts, d_workspace, workspace_bytes, st);
   Arena arena(d_workspace, workspace_bytes);
   int64_t* dlk = arena.take<int64_t>((size_t)nleft);
   int64_t* dlp = arena.take<int64_t>((size_t)nleft);
@@ -1206,7 +1351,6 @@ extern "C" int dj_distributed_inner_join_i64_host(
                                          (char*)d_workspace + off, workspace_bytes - off, stream);
   if (rc && rc != DJ_ERR_OVERFLOW) return rc;
   const int64_t n = *h_out_count < out_capacity ? *h_out_count : out_capacity;
-  int64_t* h[4]   = {h_out_lk, h_out_lp, h_out_rk, h_out_rp};
   for (int c = 0; c < 4; c++)
     DJ_CUDA_TRY(cudaMemcpyAsync(h[c], o[c], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
