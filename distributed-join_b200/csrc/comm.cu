@@ -363,6 +363,7 @@ extern "C" int dj_comm_release_workspace(dj_comm_t* c)
   return ctrl_allgather(c, &one, 1, all.data());
 }
 
+extern "C" void* dj_comm_nccl_handle(dj_comm_t* c) { return c ? (void*)c->nccl : nullptr; }
 extern "C" int dj_comm_rank(const dj_comm_t* c) { return c ? c->rank : 0; }
 extern "C" int dj_comm_size(const dj_comm_t* c) { return c ? c->size : 1; }
 

@@ -86,12 +86,16 @@ __host__ __device__ __forceinline__ uint32_t row_hash_i64(int64_t key, uint32_t 
   return h + 0x9e3779b9u;
 }
 
-// Hash used for the join's private radix sub-partitioning.  A different murmur seed makes it
-// independent of the rank-partition hash (rows on one rank share row_hash % nparts).
-constexpr uint32_t kLocalSeed = 0x2545F491u;
+// Hash used for the join's private radix sub-partitioning; the radix levels consume its TOP bits.
+// It must be independent of the rank-partition hash (rows on one rank share row_hash % nparts) but
+// is otherwise free: two 64-bit multiplies with an xor-shift between them (about half the
+// instructions of murmur3 -- the scatter kernels are issue-bound, profiles/r02a_summary.md).
 __host__ __device__ __forceinline__ uint32_t local_hash_i64(int64_t key)
 {
-  return murmur3_i64(key, kLocalSeed);
+  uint64_t x = (uint64_t)key * 0x9E3779B97F4A7C15ull;
+  x ^= x >> 29;
+  x *= 0xD6E8FEB86659FD93ull;
+  return (uint32_t)(x >> 32);
 }
 
 // Slot hash inside one shared-memory bucket: must be independent of local_hash's radix bits.

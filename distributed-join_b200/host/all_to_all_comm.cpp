@@ -161,6 +161,26 @@ void AllToAllCommunicator::launch_communication(cudf::mutable_table_view communi
   vector<AllToAllCommBuffer> buffers;
   append_to_all_to_all_comm_buffers(input_table, communicated_table, send_offsets, recv_offsets, buffers,
                                     compression_options);
+  if (auto* nc = dynamic_cast<NCCLCommunicator*>(communicator)) {
+    // NCCL backend: the whole table -- every column, every peer -- is ONE library call
+    // (dj_all_to_all: a single ncclGroup of sends/receives straight between the final buffers)
+    const int g = comm_group.size(), me = comm_group.get_local_idx();
+    vector<int> ranks(g), elem_sizes;
+    for (int i = 0; i < g; i++) ranks[i] = comm_group.get_global_rank(i);
+    vector<const void*> send_cols;
+    vector<void*> recv_cols;
+    for (auto& b : buffers) {
+      send_cols.push_back(b.send_buffer);
+      recv_cols.push_back(b.recv_buffer);
+      elem_sizes.push_back((int)cudf::size_of(b.dtype));
+    }
+    const vector<int64_t> send64(send_offsets.begin(), send_offsets.end());
+    DJ_CALL(dj_all_to_all(nc->comm, g, ranks.data(), me, send_cols.data(), recv_cols.data(), send64.data(),
+                          recv_offsets.data(), elem_sizes.data(), (int)buffers.size(),
+                          explicit_copy_to_current_rank ? 0 : 1, nc->comm_stream));
+    CUDA_RT_CALL(cudaStreamSynchronize(nc->comm_stream));
+    return;
+  }
   if (communicator->group_by_batch()) communicator->start();
   all_to_all_comm(buffers, comm_group, communicator, !explicit_copy_to_current_rank, report_timing,
                   preallocated_pinned_buffer);

@@ -3,6 +3,27 @@
 #include "bootstrap.hpp"
 #include "error.hpp"
 
+// Backend-agnostic all-gather out of the reference's own primitives: every rank sends its words
+// to every other rank inside one start()/stop() batch (device staging buffers, as send/recv
+// take device memory).
+void Communicator::allgather_i64(const int64_t* mine, int n, int64_t* all)
+{
+  int64_t* d = nullptr;
+  CUDA_RT_CALL(cudaMalloc(&d, (size_t)n * (mpi_size + 1) * sizeof(int64_t)));
+  CUDA_RT_CALL(cudaMemcpy(d, mine, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+  int64_t* d_all = d + n;
+  CUDA_RT_CALL(cudaMemcpy(d_all + (size_t)mpi_rank * n, d, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice));
+  start();
+  for (int r = 0; r < mpi_size; r++) {
+    if (r == mpi_rank) continue;
+    send(d, n, (int)sizeof(int64_t), r);
+    recv(d_all + (size_t)r * n, n, (int)sizeof(int64_t), r);
+  }
+  stop();
+  CUDA_RT_CALL(cudaMemcpy(all, d_all, (size_t)n * mpi_size * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  CUDA_RT_CALL(cudaFree(d));
+}
+
 void NCCLCommunicator::initialize()
 {
   mpi_rank = dj_bootstrap::rank();
@@ -14,6 +35,7 @@ void NCCLCommunicator::initialize()
   if (mpi_rank == 0 && mpi_size > 1) NCCL_CALL(dj_comm_unique_id(id));
   dj_bootstrap::broadcast_from_root(id, sizeof(id), "nccl_id");
   NCCL_CALL(dj_comm_create(mpi_rank, mpi_size, mpi_size > 1 ? id : nullptr, &comm));
+  nccl_comm = static_cast<ncclComm_t>(dj_comm_nccl_handle(comm));
   CUDA_RT_CALL(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
   dj_bootstrap::set_communicator(this);
 }
@@ -48,5 +70,6 @@ void NCCLCommunicator::finalize()
 {
   CUDA_RT_CALL(cudaStreamDestroy(comm_stream));
   NCCL_CALL(dj_comm_destroy(comm));
-  comm = nullptr;
+  comm      = nullptr;
+  nccl_comm = nullptr;
 }

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <cstdint>
 
@@ -22,8 +23,10 @@ class Communicator {
   virtual ~Communicator()       = default;
 
   // size exchange without MPI (replaces MPI_Isend/Irecv in communicate_sizes,
-  // src/all_to_all_comm.cpp:54-100): all-gather `n` int64 per rank
-  virtual void allgather_i64(const int64_t* mine, int n, int64_t* all) = 0;
+  // src/all_to_all_comm.cpp:54-100): all-gather `n` int64 per rank.  Not part of the reference's
+  // interface, so it is NOT pure: the default is built from start/send/recv/stop and works for
+  // any backend a user derives; NCCLCommunicator overrides it with one collective.
+  virtual void allgather_i64(const int64_t* mine, int n, int64_t* all);
 
   int mpi_rank;
   int mpi_size;
@@ -44,6 +47,7 @@ class NCCLCommunicator : public Communicator {
   bool group_by_batch() override { return true; }
   void allgather_i64(const int64_t* mine, int n, int64_t* all) override;
 
+  ncclComm_t nccl_comm     = nullptr;  // as in the reference (src/communicator.hpp:346): the raw handle
   cudaStream_t comm_stream = nullptr;  // as in the reference: the stream transfers run on
-  dj_comm_t* comm          = nullptr;  // owns the ncclComm_t
+  dj_comm_t* comm          = nullptr;  // libdj_b200's communicator object (owns nccl_comm)
 };

@@ -144,6 +144,9 @@ int dj_comm_destroy(dj_comm_t* comm);
 /* Collective.  Closes every rank's CUDA IPC mappings of the peers' join workspaces; call it on all
  * ranks before freeing or reallocating a workspace that a distributed join has used. */
 int dj_comm_release_workspace(dj_comm_t* comm);
+/* The underlying ncclComm_t (as void*; NULL for a single-rank communicator): what
+ * NCCLCommunicator::nccl_comm exposes in the reference (src/communicator.hpp:346-347). */
+void* dj_comm_nccl_handle(dj_comm_t* comm);
 int dj_comm_rank(const dj_comm_t* comm);
 int dj_comm_size(const dj_comm_t* comm);
 

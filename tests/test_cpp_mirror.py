@@ -22,7 +22,8 @@ def test_cpp_headers_mirror_reference_names():
                  "setup_memory_pool_and_communicator", "destroy_memory_pool_and_communicator",
                  "generate_tables_distributed", "generate_build_probe_tables", "ColumnCompressionOptions",
                  "generate_none_compression_options", "allocate_communicated_table", "launch_communication",
-                 "get_global_rank", "get_local_idx", "group_by_batch"]:
+                 "get_global_rank", "get_local_idx", "group_by_batch", "distribute_table", "collect_tables",
+                 "nccl_comm"]:
         assert name in text, name
 
 
@@ -72,13 +73,31 @@ def test_compare_against_analytical_single_rank():
 
 
 @pytest.mark.gpu
+def test_compare_against_single_gpu_single_rank():
+    """Port of test/compare_against_single_gpu.cu (G3) with distribute_table / collect_tables; on one rank
+    the distributed path must equal the plain single-GPU join for the whole type / odf matrix."""
+    r = _run(1, "compare_against_single_gpu")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'Test case "compare_against_single_gpu" passes successfully.' in r.stderr
+    assert r.stderr.count("passes successfully") >= 20 and "FAILED" not in r.stderr
+
+
+@pytest.mark.gpu
+def test_shuffle_on_benchmark_verifies_its_result():
+    """benchmark/shuffle_on (config 4 at a small size) checks rows, co-location and the multiset checksum."""
+    r = _run(1, "shuffle_on", "--nrows", "3000000", "--iterations", "1")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "shuffle_on check: OK" in r.stdout
+
+
+@pytest.mark.gpu
 def test_cpp_programs_multi_rank():
     import torch
 
     n = min(torch.cuda.device_count(), 8)
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    for exe in ("compare_against_analytical", "test_shuffle_on"):
+    for exe in ("compare_against_analytical", "test_shuffle_on", "compare_against_single_gpu"):
         r = _run(n, exe)
         assert r.returncode == 0, exe + r.stdout[-2000:] + r.stderr[-2000:]
         assert "passes successfully" in r.stderr
