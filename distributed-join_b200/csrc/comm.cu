@@ -75,6 +75,9 @@ constexpr int kFlagSlots = 64;      // per source rank: data flags 0..61, contro
 constexpr int kCtrlSlot  = kFlagSlots - 2;
 constexpr int kDataSlots = kFlagSlots - 2;
 constexpr int kInbox     = 4096;  // int64 words every source rank may deposit per control message
+// Messages of one join call (hello, mapping ack, bucket counts) land in separate banks of the inbox: a
+// fast rank may already send its NEXT message while a slow peer has not yet read the previous one.
+enum { kBankHello = 0, kBankAck = 1, kBankCounts = 2, kBankMisc = 3, kInboxBanks = 4 };
 constexpr size_t kSmallElems = 1 << 20;  // int64 entries of pinned + device scratch per communicator
 
 static int ensure_events(dj_comm* c, int n)
@@ -127,15 +130,20 @@ static int stream_wait_flag(dj_comm* c, cudaStream_t st, const uint32_t* d_flag,
 // flag with a stream memory operation, waits for the peers' flags and reads its inbox back.  Unlike
 // an NCCL collective it needs no SM, so it is never held up by the persistent partition / join
 // kernels that fill the GPU (an NCCL all-gather issued next to them waited for a kernel boundary:
-// 4.1 ms measured at N=2).  Safe to reuse the single inbox every call: a rank leaves a join only
-// after every peer has published its verdict, i.e. long after all inboxes of that call were read.
-static int peer_allgather(dj_comm* c, const void* src, int n, int64_t* h_all)
+// 4.1 ms measured at N=2).  Every message kind of a call has its own inbox bank (a fast rank's
+// counts must not overwrite a hello that a slow peer has not read yet); a bank is safe to reuse in
+// the next call because a rank leaves a join only after every peer has published its verdict,
+// i.e. long after all banks of that call were read.
+static int peer_allgather(dj_comm* c, int bank, const void* src, int n, int64_t* h_all)
 {
   DJ_REQUIRE(n >= 1 && n <= kInbox, "control message of %d words exceeds the inbox", n);
   cudaStream_t st    = c->ctrl_stream;
   const uint32_t seq = ++c->cseq;
-  for (int i = 0; i < c->size; i++) {
-    DJ_CUDA_TRY(cudaMemcpyAsync(c->peer_inbox[i] + (size_t)c->rank * kInbox, src, (size_t)n * 8, cudaMemcpyDefault, st));
+  const size_t bank_off = (size_t)bank * c->size * kInbox;
+  for (int k = 0; k < c->size; k++) {
+    const int i = (c->rank + k) % c->size;  // staggered: no two ranks start with the same destination
+    DJ_CUDA_TRY(cudaMemcpyAsync(c->peer_inbox[i] + bank_off + (size_t)c->rank * kInbox, src, (size_t)n * 8,
+                                cudaMemcpyDefault, st));
     if (i == c->rank) continue;
     uint32_t* flag = c->peer_flags[i] + (size_t)c->rank * kFlagSlots + kCtrlSlot;
     if (!c->flag_by_memcpy && c->fn_write32((CUstream)st, (CUdeviceptr)flag, seq, 0) != CUDA_SUCCESS)
@@ -153,7 +161,7 @@ static int peer_allgather(dj_comm* c, const void* src, int n, int64_t* h_all)
   }
   int64_t* land = c->h_pinned + (512 << 10);  // [size][n]
   DJ_REQUIRE((size_t)n * c->size <= (256u << 10), "control message too large for the landing zone");
-  DJ_CUDA_TRY(cudaMemcpy2DAsync(land, (size_t)n * 8, c->d_inbox, (size_t)kInbox * 8, (size_t)n * 8, c->size,
+  DJ_CUDA_TRY(cudaMemcpy2DAsync(land, (size_t)n * 8, c->d_inbox + bank_off, (size_t)kInbox * 8, (size_t)n * 8, c->size,
                                 cudaMemcpyDeviceToHost, st));
   DJ_CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(h_all, land, (size_t)n * c->size * 8);
@@ -191,7 +199,7 @@ static int setup_peer_exchange(dj_comm* c)
   cudaGetLastError();
 
   const size_t flag_bytes = align_up((size_t)c->size * kFlagSlots * sizeof(uint32_t), 256);
-  const size_t ctl_bytes  = flag_bytes + (size_t)c->size * kInbox * sizeof(int64_t);
+  const size_t ctl_bytes  = flag_bytes + (size_t)kInboxBanks * c->size * kInbox * sizeof(int64_t);
   DJ_CUDA_TRY(cudaMalloc(&c->d_flags, ctl_bytes));
   DJ_CUDA_TRY(cudaMemset(c->d_flags, 0, ctl_bytes));
   c->d_inbox = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(c->d_flags) + flag_bytes);
@@ -411,12 +419,13 @@ static int ctrl_allgather(dj_comm* c, const int64_t* h_mine, int n, int64_t* h_a
 }
 
 // Control all-gather of host words: kernel-free peer path when available, NCCL otherwise.
-static int ctrl_gather_host(dj_comm* c, const int64_t* h_mine, int n, int64_t* h_all)
+static int ctrl_gather_host(dj_comm* c, int bank, const int64_t* h_mine, int n, int64_t* h_all)
 {
   if (c->size > 1 && c->peer_ok && n <= kInbox) {
-    int64_t* stage = c->h_pinned + (129 << 10);  // pinned copy: the source must outlive the async copies
+    int64_t* stage = c->h_pinned + (129 << 10) + (size_t)bank * 64;  // pinned copy: outlives the async copies
+    DJ_REQUIRE(n <= 64, "host control message too long");
     memcpy(stage, h_mine, (size_t)n * 8);
-    return peer_allgather(c, stage, n, h_all);
+    return peer_allgather(c, bank, stage, n, h_all);
   }
   return ctrl_allgather(c, h_mine, n, h_all);
 }
@@ -680,7 +689,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       mine[4] = ok ? (int64_t)((CUdeviceptr)d_workspace - base) : 0;
       memcpy(&mine[5], &wh, 64);
     }
-    rc = ctrl_gather_host(comm, mine, kHello, hello.data());
+    rc = ctrl_gather_host(comm, kBankHello, mine, kHello, hello.data());
     if (rc) return rc;
   }
   auto H = [&](int r, int f) -> int64_t { return hello[(size_t)r * kHello + f]; };
@@ -720,7 +729,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   // rank's table sizes and (for the receive pieces) of the rows it receives -- so every rank can
   // compute where its rows go inside every peer without asking.
   struct WsLayout {
-    size_t count = 0, pws[2] = {0, 0}, prow[2] = {0, 0}, doff[2] = {0, 0}, dcnt[2] = {0, 0};
+    size_t count = 0, pws[2] = {0, 0}, prow[2] = {0, 0}, doff[2] = {0, 0}, dcnt[2] = {0, 0}, pbase[2] = {0, 0};
     std::vector<size_t> piece, seg_begin, seg_end, seg_parent;  // [odf*2]
     size_t join_mark = 0, need = 0;
   };
@@ -734,6 +743,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       L.pws[t]  = off_of(va.take<char>(pw));
       L.prow[t] = off_of(va.take<Row>((size_t)(n2[t] + (int64_t)nparts * kAlignRows)));
       L.doff[t] = off_of(va.take<int64_t>((size_t)nbk + 1));
+      L.pbase[t] = off_of(va.take<Row*>((size_t)nparts));
     }
     L.dcnt[0] = off_of(va.take<int64_t>((size_t)2 * nbk + 2));  // both tables' counts, contiguous: one message
     L.dcnt[1] = L.dcnt[0] + (size_t)nbk * 8;
@@ -792,7 +802,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     if (any_new) {
       // a mapping was (re)opened somewhere: agree that it worked before anybody pushes
       std::vector<int64_t> oks(world);
-      rc = ctrl_gather_host(comm, &mapped, 1, oks.data());
+      rc = ctrl_gather_host(comm, kBankAck, &mapped, 1, oks.data());
       if (rc) return rc;
       for (int r = 0; r < world; r++) use_peer = use_peer && oks[r] == 1;
       for (int r = 0; r < world; r++) memcpy(&comm->last_handle[(size_t)r * 8], &hello[(size_t)r * kHello + 5], 64);
@@ -803,6 +813,16 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   }
   trace.host("peer workspaces mapped");
   const uint32_t seq = use_peer ? ++comm->seq : 0;
+  // Exchange flavours over peer memory (identical decision on every rank: same environment):
+  //   copy   (default) partition into a local table, then copy engines push each bucket to its peer;
+  //   fused  the partition kernel's own cp.async.bulk stores write every run straight into the
+  //          destination rank's receive piece -- partition and all-to-all are ONE kernel
+  //          (src/distributed_join.cpp:211-225 + src/communicator.cpp:811-869 collapsed).
+  bool fused = false;
+  {
+    const char* e = getenv("DJ_EXCHANGE");
+    fused         = use_peer && e && (e[0] == 'f' || e[0] == 'F');
+  }
 
   // ---- 1. hash partition (src/distributed_join.cpp:213-225) on the caller's stream, as histogram
   //         halves first: the counts of BOTH tables leave for the host while the scatter kernels run.
@@ -827,7 +847,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   }
   DJ_CUDA_TRY(cudaEventRecord(comm->ev_hist, st));
   trace.mark("histograms done", st);
-  for (int t = 0; t < 2; t++) {
+  for (int t = 0; t < 2 && !fused; t++) {
     rc = pass_scatter(pstate[t], st);
     if (rc) return rc;
     DJ_CUDA_TRY(cudaEventRecord(comm->ev_part[t], st));
@@ -841,7 +861,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   DJ_CUDA_TRY(cudaStreamWaitEvent(comm->ctrl_stream, comm->ev_hist, 0));
   if (comm->peer_ok && 2 * nbk <= kInbox) {
     // device -> every peer's inbox, straight from the histogram's output: no SM, no host hop
-    rc = peer_allgather(comm, d_cnt[0], 2 * nbk, allc.data());
+    rc = peer_allgather(comm, kBankCounts, d_cnt[0], 2 * nbk, allc.data());
     if (rc) return rc;
   } else {
     int64_t* hp = comm->h_pinned + (256 << 10);  // D2H landing zone
@@ -959,8 +979,11 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       // push every peer's bucket into ITS receive piece with the copy engines (no SMs, so the
       // radix passes running meanwhile keep the whole GPU), then raise that peer's flag
       const int slot = b * 2 + t;
-      for (int i = 0; i < G; i++) {
-        if (i == rank) continue;
+      // destinations in rank+1, rank+2, ... order: at every moment the ranks push along a
+      // permutation, so no receiver sees all senders at once (the copy engines work through the
+      // peer streams roughly in issue order; starting everybody at rank 0 is an incast)
+      for (int k = 1; k < G; k++) {
+        const int i     = (rank + k) % G;
         cudaStream_t ps = comm->peer_stream[i];
         DJ_CUDA_TRY(cudaStreamWaitEvent(ps, comm->ev_part[t], 0));
         if (measure && b == 0) DJ_CUDA_TRY(cudaEventRecord(comm->ev_xbeg[(size_t)t * G + i], ps));
@@ -1015,9 +1038,60 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     rc = ensure_xevents(comm, 2 * G);
     if (rc) return rc;
   }
+  if (fused) {
+    // ---- 4'. fused partition + exchange.  Per table: the bucket cursors restart inside every
+    //          destination part (a part = this rank's slot in one peer's receive piece), the part
+    //          bases point into the peers' workspaces, the scatter kernel runs, and a flag per
+    //          (batch, table) tells every peer that this rank's rows have landed.
+    int64_t* hcur = comm->h_pinned + (700 << 10);  // [2][nbk] cursors, then [2][nparts] bases
+    int64_t* hbas = hcur + 2 * (size_t)nbk;
+    for (int t = 0; t < 2; t++) {
+      for (int q = 0; q < nparts; q++) {
+        const int b = q / G, i = q % G;
+        char* base_ws = i == rank ? wsb : peer_ws[i];
+        hbas[(size_t)t * nparts + q] =
+          (int64_t)(uintptr_t)(base_ws + lay[i].piece[(size_t)b * 2 + t] + (size_t)piece_begin(i, b, t, rank) * sizeof(Row));
+        int64_t at = 0;
+        for (int sub = 0; sub < F1s; sub++) {
+          hcur[(size_t)t * nbk + ((size_t)q << sub_bits) + sub] = at;
+          at += cnt(rank, t, q, sub);
+        }
+        if (i != rank && opts) opts->bytes_sent += (int64_t)sizeof(Row) * at;
+      }
+      Row** d_pbase = (Row**)(wsb + my.pbase[t]);
+      DJ_CUDA_TRY(cudaMemcpyAsync(pstate[t].dev.cursor, hcur + (size_t)t * nbk, (size_t)nbk * 8, cudaMemcpyHostToDevice, st));
+      DJ_CUDA_TRY(cudaMemcpyAsync(d_pbase, hbas + (size_t)t * nparts, (size_t)nparts * 8, cudaMemcpyHostToDevice, st));
+      pstate[t].dev.part_base  = d_pbase;
+      pstate[t].dev.part_shift = sub_bits;
+      if (measure) DJ_CUDA_TRY(cudaEventRecord(comm->ev_xbeg[t], st));
+      rc = pass_scatter(pstate[t], st);
+      if (rc) return rc;
+      if (measure) DJ_CUDA_TRY(cudaEventRecord(comm->ev_xend[t], st));
+      DJ_CUDA_TRY(cudaEventRecord(comm->ev_part[t], st));
+      trace.mark(t ? "partition+exchange(R) done" : "partition+exchange(L) done", st);
+      // the flags leave on the communication stream so that the next scatter is not held up
+      DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_part[t], 0));
+      for (int b = 0; b < odf; b++) {
+        for (int k = 1; k < G; k++) {
+          const int i    = (rank + k) % G;
+          uint32_t* flag = comm->peer_flags[i] + (size_t)rank * kFlagSlots + (b * 2 + t);
+          if (!comm->flag_by_memcpy &&
+              comm->fn_write32((CUstream)comm->comm_stream, (CUdeviceptr)flag, seq, 0) != CUDA_SUCCESS)
+            comm->flag_by_memcpy = true;
+          if (comm->flag_by_memcpy) {
+            uint32_t* src = reinterpret_cast<uint32_t*>(comm->h_pinned + (900 << 10)) + (seq % 4096);
+            *src          = seq;
+            DJ_CUDA_TRY(cudaMemcpyAsync(flag, src, 4, cudaMemcpyDefault, comm->comm_stream));
+          }
+        }
+        DJ_CUDA_TRY(cudaEventRecord(comm->ev_batch[(size_t)b * 2 + t], comm->comm_stream));
+      }
+    }
+    exchange_in_flight = true;
+  }
   // batch order (0,L),(0,R),(1,L),...: the left table's pushes start while the right table is
   // still being partitioned
-  for (int b = 0; b < odf; b++)
+  for (int b = 0; b < odf && !fused; b++)
     for (int t = 0; t < 2; t++) {
       if (b == 0) DJ_CUDA_TRY(cudaStreamWaitEvent(comm->comm_stream, comm->ev_part[t], 0));
       rc = issue_exchange(b, t);
@@ -1135,6 +1209,11 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     // the last push of table t complete, per peer stream; the slowest stream bounds the table
     for (int t = 0; t < 2; t++) {
       float worst = 0;
+      if (fused) {  // the scatter kernel IS the exchange
+        if (cudaEventElapsedTime(&worst, comm->ev_xbeg[t], comm->ev_xend[t]) != cudaSuccess) worst = 0;
+        opts->t_exchange_ms[t] = worst;
+        continue;
+      }
       for (int i = 0; i < G; i++) {
         if (i == rank) continue;
         float ms = 0;

@@ -71,6 +71,12 @@ struct PassDev {
   int64_t* out_pay[kMaxPayload];
   const Row* in_rows;        // row-format input (nullptr: SoA in_key / in_pay[0])
   Row* out_rows;             // row-format output (scatter_rows_kernel)
+  // Fused partition + exchange: when set, bucket k's run goes to part_base[k >> part_shift] + cursor
+  // instead of out_rows + cursor.  The bases are receive pieces -- local memory for this rank's own
+  // part, CUDA-IPC mappings of the peers' workspaces for the others -- so the scatter kernel's
+  // cp.async.bulk stores ARE the all-to-all: the TMA engine writes over NVLink.
+  Row* const* part_base;
+  int part_shift;
   int64_t in_total;          // rows in the input arrays (TMA windows are clamped to the column end)
   const int64_t* seg_begin;  // [S] first row of every input segment
   const int64_t* seg_end;    // [S] one past its last row

@@ -678,7 +678,8 @@ __global__ void __launch_bounds__(THREADS, 1) scatter_rows_kernel(PassDev d)
 
     // ---- copy-out: bucket tid's run [excl, excl+cnt) -> out_rows[gres ...)
     if (cnt) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d.out_rows + gres),
+      Row* dst = (d.part_base ? d.part_base[tid >> d.part_shift] : d.out_rows) + gres;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                    "r"(smem_u32(&s.srow[excl])), "r"((uint32_t)cnt * 16u)
                    : "memory");
     }
@@ -759,7 +760,7 @@ int launch_scatter_agg(const PassDev& dev, int F, cudaStream_t stream)
 template <int MODE>
 int launch_scatter_npay(const PassDev& dev, int npay, int F, int64_t span, cudaStream_t stream)
 {
-  if (dev.out_rows)
+  if (dev.out_rows || dev.part_base)
     return dev.in_rows ? launch_scatter_rows<MODE, true>(dev, stream) : launch_scatter_rows<MODE, false>(dev, stream);
   if (npay == 1 && span < ((int64_t)1 << 32) && use_tma_scatter())
     return F <= 32 ? launch_scatter_tma<MODE, true>(dev, stream) : launch_scatter_tma<MODE, false>(dev, stream);
@@ -851,6 +852,8 @@ int pass_histogram(const PassDesc& desc, const PassBuffers& buf, void* d_ws, siz
   }
   dev.in_rows    = buf.in_rows;
   dev.out_rows   = buf.out_rows;
+  dev.part_base  = nullptr;
+  dev.part_shift = 0;
   dev.in_total   = buf.nrows;
   dev.seg_begin  = seg_begin;
   dev.seg_end    = seg_end;

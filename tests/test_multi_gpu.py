@@ -33,6 +33,8 @@ def main():
              (500_000, 2_000_000, 0.9, False, 2), (40_000, 40_000, 1.0, True, 1), (3_000_000, 3_000_000, 0.3, True, 1),
              # BASELINE config 5 (duplicate build keys, selectivity 0.9, odf 4) at 1/8 of its per-rank size
              (12_500_000, 50_000_000, 0.9, False, 4)]
+    if os.environ.get("DJ_TEST_LIGHT"):  # short GPU leases: same shapes, smaller oracle joins
+        cases[-1] = (3_000_000, 12_000_000, 0.9, False, 4)
     for nb, np_, sel, unique, odf in cases:
         g_d = dj.gen_params(nb, np_, sel, 2 * max(nb, np_), unique)
         g_o = O.gen_params(nb, np_, sel, 2 * max(nb, np_), unique)
