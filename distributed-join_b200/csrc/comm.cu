@@ -617,6 +617,7 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
     opts->bytes_sent = 0;
     opts->workspace_needed = 0;
     opts->t_exchange_ms[0] = opts->t_exchange_ms[1] = 0;
+    opts->t_exchange_total_ms = 0;
   }
   Arena arena(d_workspace, workspace_bytes);
   int64_t* d_count = arena.take<int64_t>(32);
@@ -1205,23 +1206,32 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
       if (i != rank) DJ_CUDA_TRY(cudaStreamSynchronize(comm->peer_stream[i]));  // my buckets may be reused now
   *h_out_count = h_res[0];
   if (measure) {
-    // per-direction NVLink throughput of this rank's pushes: from "partition of table t done" to
-    // the last push of table t complete, per peer stream; the slowest stream bounds the table
+    // per-direction NVLink throughput of this rank's pushes.  The copy engines work through the
+    // peer streams one copy after the other, and an event recorded on a waiting stream is
+    // timestamped when its copy starts -- so a table's window is taken from the FIRST stream's
+    // begin event to the LATEST end event over all streams, not per stream.
+    const int first = (rank + 1) % G;
+    float latest_all = 0;
     for (int t = 0; t < 2; t++) {
       float worst = 0;
       if (fused) {  // the scatter kernel IS the exchange
         if (cudaEventElapsedTime(&worst, comm->ev_xbeg[t], comm->ev_xend[t]) != cudaSuccess) worst = 0;
         opts->t_exchange_ms[t] = worst;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, comm->ev_xbeg[0], comm->ev_xend[t]) == cudaSuccess) latest_all = std::max(latest_all, ms);
         continue;
       }
       for (int i = 0; i < G; i++) {
         if (i == rank) continue;
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, comm->ev_xbeg[(size_t)t * G + i], comm->ev_xend[(size_t)t * G + i]) == cudaSuccess)
+        if (cudaEventElapsedTime(&ms, comm->ev_xbeg[(size_t)t * G + first], comm->ev_xend[(size_t)t * G + i]) == cudaSuccess)
           worst = std::max(worst, ms);
+        if (cudaEventElapsedTime(&ms, comm->ev_xbeg[(size_t)first], comm->ev_xend[(size_t)t * G + i]) == cudaSuccess)
+          latest_all = std::max(latest_all, ms);
       }
       opts->t_exchange_ms[t] = worst;
     }
+    opts->t_exchange_total_ms = latest_all;  // first push of the left table -> last push of the right table
     cudaGetLastError();
   }
   trace.dump(rank);

@@ -239,18 +239,7 @@ __device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint3
     : "memory");
 }
 
-// 16-byte aligned window covering n int64 starting at p
-struct Window {
-  const char* base;
-  uint32_t bytes;
-};
-__device__ __forceinline__ Window window_of(const int64_t* p, int n)
-{
-  const uintptr_t a  = reinterpret_cast<uintptr_t>(p);
-  const uintptr_t lo = a & ~(uintptr_t)15;
-  const uintptr_t hi = (a + (uintptr_t)n * 8 + 15) & ~(uintptr_t)15;
-  return Window{reinterpret_cast<const char*>(lo), (uint32_t)(hi - lo)};
-}
+// position of row p inside the 16-byte aligned window staged for it (partition.cu: stage_column)
 __device__ __forceinline__ int skip_of(const int64_t* p)
 {
   return (int)((reinterpret_cast<uintptr_t>(p) & 15) >> 3);

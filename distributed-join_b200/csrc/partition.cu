@@ -336,8 +336,11 @@ struct TileDesc {
 // Stages rows [beg, beg+n) of an 8-byte column: the TMA source must be 16-byte aligned, so the copy
 // covers the aligned window around the rows (row `beg` lands at smem_dst[skip_of(col + beg)]).
 // The window never leaves the column: when the column's last row sits in the low half of a
-// 16-byte word, that row is copied by hand instead (a generic-proxy store by the issuing
-// thread, ordered before its mbarrier arrive).  Returns the bytes the TMA will deliver.
+// 16-byte word, that row is copied by hand instead.  Two calls per tile and column:
+//   issue == false  returns the bytes the TMA will deliver and performs the hand copy -- a plain
+//                   shared-memory store by the issuing thread, BEFORE its mbarrier arrive
+//                   (release), so consumers that pass the barrier see it;
+//   issue == true   issues the TMA copy.
 __device__ __forceinline__ uint32_t stage_column(int64_t* smem_dst, const int64_t* col, int64_t beg, int n,
                                                  int64_t col_rows, unsigned long long* bar, bool issue)
 {
@@ -347,7 +350,7 @@ __device__ __forceinline__ uint32_t stage_column(int64_t* smem_dst, const int64_
   const uintptr_t end = reinterpret_cast<uintptr_t>(col + col_rows);
   if (hi > end) {
     hi -= 16;
-    if (issue) smem_dst[(hi - lo) >> 3] = col[beg + n - 1];
+    if (!issue) smem_dst[(hi - lo) >> 3] = col[beg + n - 1];
   }
   const uint32_t bytes = (uint32_t)(hi - lo);
   if (issue && bytes) tma_load(smem_dst, reinterpret_cast<const void*>(lo), bytes, bar);

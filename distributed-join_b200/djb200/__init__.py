@@ -55,6 +55,7 @@ class JoinOptions(C.Structure):
         ("measure_exchange", C.c_int),
         ("pad_", C.c_int),
         ("t_exchange_ms", C.c_double * 2),
+        ("t_exchange_total_ms", C.c_double),
     ]
 
 

@@ -8,6 +8,8 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "communicator.hpp"
@@ -52,7 +54,9 @@ static std::string rendezvous_path(const char* tag)
   std::string p    = dir ? dir : "/tmp";
   p += "/dj_b200_";
   p += job ? job : (port ? port : "default");
-  p += "_";
+  // every rank of one launch has the same parent (the launcher's agent): a per-launch nonce, so a
+  // file left behind by a killed run on the same port can never be mistaken for this run's
+  p += "_" + std::to_string((long)::getppid()) + "_";
   p += tag;
   return p;
 }
@@ -62,18 +66,23 @@ void broadcast_from_root(void* buf, std::size_t bytes, const char* tag)
   if (g_size == 1) return;
   const std::string path = rendezvous_path(tag), tmp = path + ".tmp";
   if (g_rank == 0) {
-    FILE* f = std::fopen(tmp.c_str(), "wb");
-    CHECK_ERROR(f != nullptr, true, "open rendezvous file");
-    CHECK_ERROR(std::fwrite(buf, 1, bytes, f) == bytes, true, "write rendezvous file");
-    std::fclose(f);
+    // fresh private file (never follows a planted symlink), published atomically by rename
+    ::unlink(path.c_str());
+    ::unlink(tmp.c_str());
+    const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+    CHECK_ERROR(fd >= 0, true, "open rendezvous file");
+    CHECK_ERROR(::write(fd, buf, bytes) == (ssize_t)bytes, true, "write rendezvous file");
+    ::close(fd);
     CHECK_ERROR(std::rename(tmp.c_str(), path.c_str()), 0, "publish rendezvous file");
   } else {
     for (int tries = 0;; tries++) {
-      FILE* f = std::fopen(path.c_str(), "rb");
-      if (f) {
-        const std::size_t got = std::fread(buf, 1, bytes, f);
-        std::fclose(f);
-        if (got == bytes) break;
+      const int fd = ::open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+      if (fd >= 0) {
+        struct stat sb;
+        const bool mine = ::fstat(fd, &sb) == 0 && sb.st_uid == ::getuid() && S_ISREG(sb.st_mode);
+        const ssize_t got = mine ? ::read(fd, buf, bytes) : -1;
+        ::close(fd);
+        if (got == (ssize_t)bytes) break;
       }
       if (tries > 60000) {
         std::fprintf(stderr, "ERROR: rank %d timed out waiting for %s\n", g_rank, path.c_str());

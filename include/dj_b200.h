@@ -196,8 +196,9 @@ typedef struct {
                                returns the error together, so callers can grow and retry)      */
   int measure_exchange;  /* in: time this rank's NVLink pushes with CUDA events                */
   int pad_;
-  double t_exchange_ms[2]; /* out (measure_exchange): per table, from "partition done" to the
-                              last push complete on the slowest peer stream                    */
+  double t_exchange_ms[2]; /* out (measure_exchange): per table, from its first push starting to
+                              its last push complete (over all peer streams)                   */
+  double t_exchange_total_ms; /* out: first push of the left table -> last push of the right     */
 } dj_join_options;
 
 size_t dj_distributed_inner_join_workspace_bytes(int64_t nleft, int64_t nright, int world,

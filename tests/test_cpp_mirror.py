@@ -52,6 +52,21 @@ def test_communication_group_semantics():
     assert members == [1, 3, 5, 7] and idx == 2
 
 
+def test_bootstrap_rendezvous_two_ranks(tmp_path):
+    """CPU: the MPI-free ncclUniqueId broadcast (host/bootstrap.cpp): ranks started by one parent agree on
+    rank 0's bytes; a stale file of an earlier launch on the same port is never picked up (per-launch nonce)."""
+    exe = os.path.join(BIN, "test_bootstrap")
+    if not os.path.exists(exe):
+        pytest.skip("bin/test_bootstrap not built")
+    for salt in ("A", "B"):  # two launches on the same port; each has its own parent, like two torchrun agents
+        env = dict(os.environ, WORLD_SIZE="2", MASTER_PORT="29999", DJ_RENDEZVOUS_DIR=str(tmp_path))
+        r = subprocess.run(["sh", "-c", f"RANK=1 {exe} {salt} & RANK=0 {exe} {salt}; wait"], env=env,
+                           capture_output=True, text=True, timeout=60)
+        outs = sorted(line.split() for line in r.stdout.strip().splitlines())
+        assert r.returncode == 0 and len(outs) == 2, r.stdout + r.stderr
+        assert outs[0][0] == "0" and outs[1][0] == "1" and outs[0][2] == outs[1][2]
+
+
 def _run(nproc, exe, *args):
     if nproc == 1:
         return subprocess.run([os.path.join(BIN, exe), *args], cwd=ROOT, capture_output=True, text=True, timeout=300,
