@@ -1257,13 +1257,17 @@ extern "C" int dj_distributed_inner_join_i64(dj_comm_t* comm, const int64_t* d_l
   return DJ_OK;
 }
 
+static size_t streamed_ws_bytes(int64_t nleft, int64_t nright, int64_t out_capacity);
+
 extern "C" size_t dj_distributed_inner_join_host_workspace_bytes(int64_t nleft, int64_t nright,
                                                                  int64_t out_capacity, int world,
                                                                  int over_decom_factor)
 {
-  return dj_distributed_inner_join_workspace_bytes(nleft, nright, world, over_decom_factor) +
-         2 * (align_up((size_t)nleft * 8, 256) + align_up((size_t)nright * 8, 256)) +
-         4 * align_up((size_t)out_capacity * 8, 256) + 8192;
+  const size_t staged = dj_distributed_inner_join_workspace_bytes(nleft, nright, world, over_decom_factor) +
+                        2 * (align_up((size_t)nleft * 8, 256) + align_up((size_t)nright * 8, 256)) +
+                        4 * align_up((size_t)out_capacity * 8, 256) + 8192;
+  if (world > 1) return staged;
+  return std::max(staged, streamed_ws_bytes(nleft, nright, out_capacity));
 }
 
 // Single-GPU end-to-end join with HOST tables, streamed: the PCIe link is the bottleneck (25.6 GB in,
@@ -1276,6 +1280,40 @@ extern "C" size_t dj_distributed_inner_join_host_workspace_bytes(int64_t nleft, 
 //      re-inserts the build rows once per chunk, which costs HBM bandwidth that is idle anyway;
 //   3. each chunk's matches go down on their own stream while the next chunk comes up (full duplex).
 // What is left after the last byte has arrived is one chunk's join and one chunk's matches.
+struct StreamedShape {
+  bool swap;
+  int64_t nb, np, chunk;
+  int nchunks;
+  RadixPlan plan;
+};
+static StreamedShape streamed_shape(int64_t nleft, int64_t nright)
+{
+  StreamedShape s{};
+  s.swap      = build_on_right(nleft, nright);
+  s.nb        = s.swap ? nright : nleft;
+  s.np        = s.swap ? nleft : nright;
+  s.plan      = plan_for(s.nb > 0 ? s.nb : 1, false);
+  int nchunks = 16;
+  const char* e = getenv("DJ_HOST_CHUNKS");
+  if (e && atoi(e) > 0) nchunks = atoi(e);
+  int64_t chunk = (s.np + nchunks - 1) / nchunks;
+  if (chunk < (1 << 20)) chunk = std::min<int64_t>(s.np, 1 << 20);  // small tables: few chunks
+  chunk     = std::max<int64_t>((chunk + 1) / 2 * 2, 2);  // even row counts keep the host columns 16-byte aligned
+  s.chunk   = chunk;
+  s.nchunks = (int)std::max<int64_t>((s.np + chunk - 1) / chunk, 1);
+  return s;
+}
+// device bytes host_join_streamed takes from the workspace (same arithmetic as its arena walk)
+static size_t streamed_ws_bytes(int64_t nleft, int64_t nright, int64_t out_capacity)
+{
+  const StreamedShape s = streamed_shape(nleft, nright);
+  size_t total = 256 + 2 * align_up((size_t)s.nb * 8, 256);
+  total += (s.nchunks > 1 ? 4 : 2) * align_up((size_t)s.chunk * 8, 256);
+  total += 4 * align_up((size_t)out_capacity * 8, 256);
+  total += side_ws_bytes(s.nb, s.plan, 0) + side_ws_bytes(s.chunk, s.plan, 0);
+  return total + (64 << 10);
+}
+
 static int host_join_streamed(const int64_t* h_left_key, const int64_t* h_left_payload, int64_t nleft,
                               const int64_t* h_right_key, const int64_t* h_right_payload, int64_t nright,
                               int64_t* const h_out[4], int64_t out_capacity, int64_t* h_out_count,
@@ -1287,22 +1325,15 @@ static int host_join_streamed(const int64_t* h_left_key, const int64_t* h_left_p
     opts->bytes_sent = opts->workspace_needed = 0;
   }
   if (nleft == 0 || nright == 0) return DJ_OK;  // src/distributed_join.cpp:76-82
-  const bool swap      = build_on_right(nleft, nright);
-  const int64_t nb     = swap ? nright : nleft, np = swap ? nleft : nright;
+  const StreamedShape shape = streamed_shape(nleft, nright);
+  const bool swap      = shape.swap;
+  const int64_t nb     = shape.nb, np = shape.np, chunk = shape.chunk;
+  const int nchunks    = shape.nchunks;
   const int64_t* h_bk  = swap ? h_right_key : h_left_key;
   const int64_t* h_bp  = swap ? h_right_payload : h_left_payload;
   const int64_t* h_pk  = swap ? h_left_key : h_right_key;
   const int64_t* h_pp  = swap ? h_left_payload : h_right_payload;
-  const RadixPlan plan = plan_for(nb, false);
-  int nchunks          = 16;
-  {
-    const char* e = getenv("DJ_HOST_CHUNKS");
-    if (e && atoi(e) > 0) nchunks = atoi(e);
-  }
-  int64_t chunk = (np + nchunks - 1) / nchunks;
-  if (chunk < (1 << 20)) chunk = std::min<int64_t>(np, 1 << 20);  // small tables: few chunks
-  chunk   = (chunk + 1) / 2 * 2;  // even row counts keep every chunk's host columns 16-byte aligned
-  nchunks = (int)((np + chunk - 1) / chunk);
+  const RadixPlan plan = shape.plan;
   int64_t* h_cnt = nullptr;  // pinned: running match count after every chunk (allocated before any work is queued)
   DJ_CUDA_TRY(cudaMallocHost(&h_cnt, (size_t)(nchunks + 1) * 8));
   struct PinGuard {
@@ -1322,7 +1353,9 @@ static int host_join_streamed(const int64_t* h_left_key, const int64_t* h_left_p
   int64_t* o[4];
   for (int c = 0; c < 4; c++) o[c] = arena.take<int64_t>((size_t)out_capacity);
   if (!d_count || !dbk || !dbp || !dck[1] || !dcp[1] || !o[3]) {
-    set_error("distributed_inner_join_host: workspace too small");
+    set_error("distributed_inner_join_host: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              streamed_ws_bytes(nleft, nright, out_capacity));
+    if (opts) opts->workspace_needed = (int64_t)streamed_ws_bytes(nleft, nright, out_capacity);
     return DJ_ERR_WORKSPACE;
   }
   cudaStream_t up = nullptr, down = nullptr;

@@ -149,3 +149,23 @@ def test_omp_baseline_agrees(oracle):
     r = oracle.partitioned_join_omp(bk, bp, pk, pp, nparts=64, checksum=True)
     n, cols = oracle.inner_join(bk, bp, pk, pp)
     assert r["n_out"] == n and r["checksum"] == oracle.multiset_checksum4(*cols)
+
+
+def test_generate_global_tables_is_the_union_of_every_ranks_tables(oracle):
+    """bench.py's parity oracle regenerates the GLOBAL tables in one go: they must be exactly the rows the
+    ranks hold after generate_tables_distributed (src/generate_table.cuh:155-272), for unique and
+    duplicate build keys, and their join must equal the join of the concatenated per-rank tables."""
+    import numpy as np
+
+    for unique, sel, world in ((True, 0.3, 4), (False, 0.9, 2)):
+        g = oracle.gen_params(20_000, 30_000, sel, 60_000, unique)
+        (bk, bp), (pk, pp), hits = oracle.generate_global_tables(g, world)
+        tabs = [oracle.generate_tables_distributed(g, r, world) for r in range(world)]
+        cat = [np.concatenate([t[i][j] for t in tabs]) for i in (0, 1) for j in (0, 1)]
+        for got, want in zip((bk, bp, pk, pp), cat):
+            assert (np.sort(got) == np.sort(want)).all()
+        n_ref, ref = oracle.inner_join(*cat)
+        r = oracle.partitioned_join_omp(bk, bp, pk, pp, nparts=64, checksum=True)
+        assert r["n_out"] == n_ref and r["checksum"] == oracle.multiset_checksum4(*ref)
+        if unique:
+            assert n_ref == hits
