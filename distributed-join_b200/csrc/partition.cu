@@ -547,10 +547,18 @@ struct __align__(128) ScatterRowsSmem {
   int warp_sums[32];
 };
 
-template <int MODE, bool IN_ROWS, int THREADS, int RPT>
+// LEAN (default): three CTA barriers per tile instead of four -- bucket starts are assembled from the
+// in-warp prefix (shared memory) plus the prefix over warp totals, which every warp keeps in
+// registers (lane l holds the prefix of warp l) and reads with a shuffle -- and the tile producer is
+// lane 0 of the LAST warp, which owns the fewest buckets, so its dependent descriptor loads are off
+// the other warps' critical path.  LEAN == false is the first version of the kernel, kept selectable
+// (DJ_SCATTER_LEAN=0).
+template <int MODE, bool IN_ROWS, int THREADS, int RPT, bool LEAN>
 __global__ void __launch_bounds__(THREADS, 1) scatter_rows_kernel(PassDev d)
 {
   static_assert(THREADS >= kMaxFanout, "one thread owns one bucket");
+  static_assert(!LEAN || THREADS == 1024, "LEAN keeps one warp-total prefix per lane: exactly 32 warps");
+  constexpr int kProducer = LEAN ? THREADS - 32 : 0;
   using Smem = ScatterRowsSmem<THREADS, RPT, IN_ROWS>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& s         = *reinterpret_cast<Smem*>(smem_raw);
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(THREADS, 1) scatter_rows_kernel(PassDev d)
     }
   };
 
-  if (tid == 0) {
+  if (tid == kProducer) {
     mbar_init(&s.full[0], 1);
     mbar_init(&s.full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -634,6 +642,7 @@ __global__ void __launch_bounds__(THREADS, 1) scatter_rows_kernel(PassDev d)
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
       const int r = j * THREADS + tid;
+      brank[j]    = 0;
       if (r < tile_n) {
         const int b = bucket_of<MODE>(key[j], d);
         brank[j]    = ((uint32_t)b << 16) | (uint32_t)atomicAdd(&cnt_cur[b], 1);
@@ -641,7 +650,7 @@ __global__ void __launch_bounds__(THREADS, 1) scatter_rows_kernel(PassDev d)
     }
     __syncthreads();  // (A) tile histogram complete; the input stage has been read
 
-    if (tid == 0) issue_tile(k + 2);  // refill this stage right away: the rows live in registers
+    if (tid == kProducer) issue_tile(k + 2);  // refill this stage right away: the rows live in registers
 
     // ---- reserve + scan (thread b owns bucket b)
     const int cnt = tid < F ? cnt_cur[tid] : 0;
@@ -655,22 +664,40 @@ __global__ void __launch_bounds__(THREADS, 1) scatter_rows_kernel(PassDev d)
       if (lane >= o) incl += t;
     }
     if (lane == 31) s.warp_sums[warp] = incl;
+    if (LEAN && tid < F) s.s_start[tid] = incl - cnt;  // prefix inside the owning warp only
     // the previous tile's bulk copies must have read the sorted tile before it is overwritten
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();  // (B)
-    int wbase = lane < warp ? s.warp_sums[lane] : 0;
+    int excl;
+    int wpre = 0;  // LEAN: lane l holds the exclusive prefix of the warp totals up to warp l
+    if (LEAN) {
+      const int wsum = s.warp_sums[lane];
+      int winc       = wsum;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wbase += __shfl_xor_sync(0xffffffffu, wbase, o);
-    const int excl = wbase + incl - cnt;
-    if (tid < F) s.s_start[tid] = excl;
-    __syncthreads();  // (C)
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      wpre = winc - wsum;
+      excl = __shfl_sync(0xffffffffu, wpre, warp) + incl - cnt;
+    } else {
+      int wbase = lane < warp ? s.warp_sums[lane] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wbase += __shfl_xor_sync(0xffffffffu, wbase, o);
+      excl = wbase + incl - cnt;
+      if (tid < F) s.s_start[tid] = excl;
+      __syncthreads();  // (C)
+    }
 
     // ---- sort: one STS.128 per row
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
       const int r = j * THREADS + tid;
+      const int b = (int)(brank[j] >> 16);
+      // bucket start = prefix of the warps before the bucket's owner + prefix inside that warp
+      const int wb = LEAN ? __shfl_sync(0xffffffffu, wpre, b >> 5) : 0;  // every lane takes part
       if (r < tile_n) {
-        const int pos = s.s_start[brank[j] >> 16] + (int)(brank[j] & 0xffffu);
+        const int pos = wb + s.s_start[b] + (int)(brank[j] & 0xffffu);
         *reinterpret_cast<int4*>(&s.srow[pos]) =
           make_int4((int)(uint32_t)(uint64_t)key[j], (int)((uint64_t)key[j] >> 32),
                     (int)(uint32_t)(uint64_t)pay[j], (int)((uint64_t)pay[j] >> 32));
@@ -716,12 +743,22 @@ int launch_scatter_tma(const PassDev& dev, cudaStream_t stream)
   return DJ_OK;
 }
 
-template <int MODE, bool IN_ROWS>
-int launch_scatter_rows(const PassDev& dev, cudaStream_t stream)
+bool scatter_lean()
+{
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DJ_SCATTER_LEAN");
+    v             = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int MODE, bool IN_ROWS, bool LEAN>
+int launch_scatter_rows_impl(const PassDev& dev, cudaStream_t stream)
 {
   constexpr int THREADS = 1024, RPT = 4;
   const size_t smem = sizeof(ScatterRowsSmem<THREADS, RPT, IN_ROWS>);
-  auto kern         = scatter_rows_kernel<MODE, IN_ROWS, THREADS, RPT>;
+  auto kern         = scatter_rows_kernel<MODE, IN_ROWS, THREADS, RPT, LEAN>;
   DJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope prof(DJ_PROF_SCATTER, stream);
@@ -729,6 +766,13 @@ int launch_scatter_rows(const PassDev& dev, cudaStream_t stream)
   }
   DJ_LAUNCH_CHECK();
   return DJ_OK;
+}
+
+template <int MODE, bool IN_ROWS>
+int launch_scatter_rows(const PassDev& dev, cudaStream_t stream)
+{
+  return scatter_lean() ? launch_scatter_rows_impl<MODE, IN_ROWS, true>(dev, stream)
+                        : launch_scatter_rows_impl<MODE, IN_ROWS, false>(dev, stream);
 }
 
 size_t scatter_smem_bytes(int npay, int F)
