@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) scatter_tma_kernel(PassDev d)
 //   copy-out the thread owning bucket b issues ONE cp.async.bulk shared->global for the run
 //            (16-byte aligned on both sides because rows are 16 bytes): the TMA engine streams the
 //            tile out while the CTA already ranks the next tile.  No LDS/STG for the write-out.
-// Four CTA barriers per tile.  The sorted tile is single-buffered: cp.async.bulk.wait_group.read
+// Three CTA barriers per tile (four in the LEAN == false variant).  The sorted tile is single-buffered: cp.async.bulk.wait_group.read
 // (shared-memory side of the copies done) is awaited just before the next tile's sort.
 template <int THREADS, int RPT, bool IN_ROWS>
 struct __align__(128) ScatterRowsSmem {
