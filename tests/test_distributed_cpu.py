@@ -46,3 +46,18 @@ def test_bench_reference_arm_under_torchrun_prints_one_line(monkeypatch):
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_import_does_not_pin_openmp():
+    """Regression: OMP_PROC_BIND / OMP_PLACES exported at import time pinned EVERY rank's main thread to core 0
+    (libgomp binds the initial thread): 105 instead of 9.5 ms/step at N=8.  They may only be set by the
+    process that runs a CPU leg, right before the oracle is loaded."""
+    import subprocess
+    import sys
+
+    code = ("import os, sys; os.environ.pop('OMP_PROC_BIND', None); os.environ.pop('OMP_PLACES', None); "
+            "sys.argv=['bench.py']; import bench; "
+            "assert 'OMP_PROC_BIND' not in os.environ and 'OMP_PLACES' not in os.environ; "
+            "bench.pin_openmp_for_cpu_arm(); assert os.environ['OMP_PROC_BIND'] == 'close'; print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
